@@ -1,0 +1,246 @@
+"""``COINNLocal`` - the site-side, re-entrant state machine driven once per engine round.
+
+Protocol parity: coinstac_dinunet/distrib/nodes/local.py:29-295 and the round table in
+SURVEY §3.0 (phases, JSON keys, file names, artefact layout).  The class is stateless between
+rounds - everything persistent lives in ``cache`` (quirk §8.5-17).
+
+Transport: with ``cache['transport'] == 'file'`` (default) one round == one optimizer step,
+exactly like the reference.  With ``'nvlink'``/``'nccl'`` the learner runs *a whole local epoch*
+of fused steps per round (gradient exchange inside the kernel) and the JSON control plane is
+touched once per epoch.
+"""
+import json as _json
+import os as _os
+import shutil as _shutil
+import time as _time
+import traceback as _tback
+from os import sep as _sep
+from typing import List as _List
+
+from ... import config as _conf
+from ... import utils as _utils
+from ...config.keys import AGG_Engine, Key, Mode, Phase, Transport
+from ...data import COINNDataHandle as _DataHandle
+from ...utils import FrozenDict as _FrozenDict
+from ..learner import COINNLearner as _dSGDLearner
+
+
+def _engine_learners():
+    from ..powersgd import PowerSGDLearner
+    from ..rankdad import DADLearner
+    return {AGG_Engine.dSGD: _dSGDLearner, AGG_Engine.rankDAD: DADLearner, AGG_Engine.powerSGD: PowerSGDLearner}
+
+
+class COINNLocal:
+    _PROMPT_TASK_ = "Task id must be given."
+    _PROMPT_MODE_ = f"Mode must be provided and should be one of {[Mode.TRAIN.value, Mode.TEST.value]}."
+
+    def __init__(self, cache: dict = None, input: dict = None, state: dict = None,
+                 task_id='nn_task', mode: str = None, batch_size: int = 8, local_iterations: int = 1,
+                 epochs: int = 31, validation_epochs: int = 1, learning_rate: float = 0.001,
+                 gpus: _List[int] = None, pin_memory: bool = False, num_workers: int = 0,
+                 load_limit: int = _conf.max_size, load_sparse=False, pretrained_path: str = None,
+                 patience: int = None, num_folds: int = None, split_ratio=None,
+                 pretrain_args: dict = None, dataloader_args: dict = None, verbose=False,
+                 monitor_metric='f1', metric_direction='maximize', log_header='Loss|Accuracy,F1',
+                 agg_engine='dSGD', num_reducers=2, precision_bits=32, **kw):
+        self.out = {}
+        self.cache = cache
+        self.input = _FrozenDict(input)
+        self.state = _FrozenDict(state)
+
+        defaults = dict(
+            task_id=task_id, mode=mode, batch_size=batch_size, local_iterations=local_iterations,
+            epochs=epochs, validation_epochs=validation_epochs, learning_rate=learning_rate, gpus=gpus,
+            pin_memory=pin_memory, num_workers=num_workers, load_limit=load_limit, load_sparse=load_sparse,
+            pretrained_path=pretrained_path, patience=patience if patience else epochs,
+            split_ratio=split_ratio, num_folds=num_folds, verbose=verbose, monitor_metric=monitor_metric,
+            metric_direction=metric_direction, log_header=log_header, agg_engine=agg_engine,
+            num_reducers=num_reducers, precision_bits=precision_bits)
+        defaults.update(**kw)
+        self._args = _FrozenDict(defaults)
+        self._pretrain_args = pretrain_args if pretrain_args else {}
+        self._dataloader_args = dataloader_args if dataloader_args else {}
+
+        if not self.cache.get(Key.ARGS_CACHED):
+            self._cache_args_once()
+
+    def _cache_args_once(self):
+        """Merge configuration into ``cache`` exactly once, highest priority first:
+        ``input`` → ``input['<task>_args']`` → ``input['<engine>_args']`` →
+        ``input['<task>_data_conf']`` (only keys the two arg groups did not set) →
+        constructor defaults for whatever is still ``None`` (ref local.py:93-117)."""
+        inp = self.input
+        self.cache.update(**inp)
+        task_args = inp.get(f"{inp.get('task_id')}_args", {})
+        engine_args = inp.get(f"{inp.get('agg_engine')}_args", {})
+        self.cache.update(**task_args)
+        self.cache.update(**engine_args)
+        for k, v in inp.get(f"{inp.get('task_id')}_data_conf", {}).items():
+            if k not in task_args and k not in engine_args:
+                self.cache[k] = v
+        for k, v in self._args.items():
+            if self.cache.get(k) is None:
+                self.cache[k] = v
+
+        assert self.cache['task_id'] is not None, self._PROMPT_TASK_
+        assert self.cache['mode'] in (Mode.TRAIN, Mode.TEST), self._PROMPT_MODE_
+        if self.cache['mode'] == Mode.TRAIN:
+            assert self.cache['split_ratio'] or self.cache['num_folds'], \
+                "Split ratio or K(num k-folds) is needed."
+        self.cache[Key.ARGS_CACHED] = True
+
+    # ------------------------------------------------------------ phase handlers
+    def _init_runs(self, trainer):
+        out = {}
+        out.update(trainer.data_handle.prepare_data())
+        self.cache['num_folds'] = len(self.cache['splits'])
+        trainer.init_nn(set_devices=True)
+
+        out['data_size'] = {}
+        for fold, name in self.cache['splits'].items():
+            with open(self.cache['split_dir'] + _sep + name) as fp:
+                split = _json.loads(fp.read())
+            out['data_size'][fold] = {part: len(files) for part, files in split.items()}
+        return out
+
+    def _next_run(self, trainer):
+        self.cache.update(cursor=0)
+        self.cache[Key.TRAIN_SERIALIZABLE] = []
+        ix = self.cache['split_ix']
+        self.cache['split_file'] = self.cache['splits'][ix]
+        self.cache['log_dir'] = _os.path.join(self.state['outputDirectory'], self.cache['task_id'], f"fold_{ix}")
+        _os.makedirs(self.cache['log_dir'], exist_ok=True)
+
+        # a new fold starts from scratch: drop engine state that is tied to the old modules
+        for stale in ('_arena', '_graph_step', 'powerSGD_state', 'local_epoch'):
+            self.cache.pop(stale, None)
+        trainer.init_nn(init_model=True, init_optim=True, set_devices=True, init_weights=True)
+        self.cache['best_nn_state'] = f"best.{self.cache['task_id']}-{ix}.pt"
+        self.cache['latest_nn_state'] = f"latest.{self.cache['task_id']}-{ix}.pt"
+        return {'phase': Phase.COMPUTATION}
+
+    def _pretrain_local(self, trainer_cls, datahandle_cls, train_dataset, validation_dataset):
+        """Optional single-site warm-up on the site holding the most data (chosen by the
+        remote via ``global_runs[site]['pretrain']``); its best weights are then broadcast."""
+        out = {'phase': Phase.COMPUTATION}
+        wants = self._pretrain_args.get('epochs', 0) > 0
+        if wants and self.cache.get('pretrain'):
+            overrides = dict(self.cache.get('pretrain_args') or self._pretrain_args)
+            saved = {k: self.cache.get(k) for k in overrides}
+            self.cache.update(overrides)  # quirk §8.5-4 fixed: pretrain args really apply
+            try:
+                trainer = trainer_cls(data_handle=datahandle_cls(
+                    cache=self.cache, input=self.input, state=self.state, dataloader_args=self._dataloader_args))
+                trainer.init_nn()
+                trainer.init_training_cache()
+                out.update(**trainer.train_local(train_dataset, validation_dataset))
+            finally:
+                for k, v in saved.items():
+                    if v is None:
+                        self.cache.pop(k, None)
+                    else:
+                        self.cache[k] = v
+            out['phase'] = Phase.PRE_COMPUTATION
+        if wants and any(r.get('pretrain') for r in self.input['global_runs'].values()):
+            out['phase'] = Phase.PRE_COMPUTATION
+        return out
+
+    # ------------------------------------------------------------------ compute
+    def compute(self, mp_pool, trainer_cls, dataset_cls=None, datahandle_cls=_DataHandle,
+                learner_cls=_dSGDLearner, **kw):
+        trainer = trainer_cls(data_handle=datahandle_cls(
+            cache=self.cache, input=self.input, state=self.state, dataloader_args=self._dataloader_args))
+
+        phase = self.out['phase'] = self.input.get('phase', Phase.INIT_RUNS)
+        if phase == Phase.INIT_RUNS:
+            self.out.update(**self._init_runs(trainer))
+            # share the constructor-level arguments with the aggregator and freeze them
+            shared = {k: self.cache[k] for k in self._args}
+            # also share what the aggregator needs to build the same metric objects
+            for k in ('num_class', *self.cache.get('shared_keys', ())):
+                if k in self.cache and k not in shared:
+                    shared[k] = self.cache[k]
+            self.cache['frozen_args'] = _FrozenDict(shared)
+            self.out['shared_args'] = self.cache['frozen_args']
+
+        elif phase == Phase.NEXT_RUN:
+            self.cache.update(**self.input['global_runs'][self.state['clientId']])
+            self.out.update(**self._next_run(trainer))
+            if self.cache['mode'] == Mode.TRAIN:
+                self.out.update(**self._pretrain_local(
+                    trainer_cls, datahandle_cls,
+                    trainer.data_handle.get_train_dataset(dataset_cls),
+                    trainer.data_handle.get_validation_dataset(dataset_cls)))
+
+        elif phase == Phase.PRE_COMPUTATION and self.input.get('pretrained_weights'):
+            trainer.load_checkpoint(file_path=self.state['baseDirectory'] + _sep + self.input['pretrained_weights'])
+            self.out['phase'] = Phase.COMPUTATION
+
+        learner = self._get_learner_cls(learner_cls)(trainer=trainer, mp_pool=mp_pool)
+        self.out['mode'] = learner.global_modes.get(self.state['clientId'], self.cache['mode'])
+
+        if self.out['phase'] == Phase.COMPUTATION:
+            self._computation_round(trainer, learner, dataset_cls)
+        elif self.out['phase'] == Phase.SUCCESS:
+            self._collect_results()
+
+    def _computation_round(self, trainer, learner, dataset_cls):
+        modes = list(learner.global_modes.values())
+        if self.input.get('save_current_as_best'):
+            learner.trainer.save_checkpoint(file_path=self.cache['log_dir'] + _sep + self.cache['best_nn_state'])
+
+        if self.input.get('update'):
+            self.out.update(**learner.step())
+
+        if any(m == Mode.TRAIN for m in modes):
+            # Lagging sites re-shuffle and keep contributing until *everyone* is waiting.
+            it, out = learner.to_reduce()
+            self.out.update(**out)
+            if it.get('averages') and it.get('metrics'):
+                self.cache[Key.TRAIN_SERIALIZABLE].append(
+                    {'averages': it['averages'].serialize(), 'metrics': it['metrics'].serialize()})
+                self.out.update(**trainer.on_iteration_end(0, 0, it))
+
+        if modes and all(m == Mode.VALIDATION for m in modes):
+            self.out.update(**trainer.validation_distributed(dataset_cls))
+            self.out[Key.TRAIN_SERIALIZABLE] = self.cache[Key.TRAIN_SERIALIZABLE]
+            self.cache[Key.TRAIN_SERIALIZABLE] = []
+            self.out['mode'] = Mode.TRAIN_WAITING
+
+        if modes and all(m == Mode.TEST for m in modes):
+            self.out.update(**trainer.test_distributed(dataset_cls))
+            self.out['mode'] = self.cache['frozen_args']['mode']
+            self.out['phase'] = Phase.NEXT_RUN_WAITING
+            trainer.save_checkpoint(file_path=self.cache['log_dir'] + _sep + self.cache['latest_nn_state'])
+            _utils.save_cache(self.cache, self.cache['log_dir'])
+
+    def _collect_results(self):
+        """Final round: pick up the results zip broadcast by the aggregator (retry x3)."""
+        name = f"{self.input['results_zip']}.zip"
+        src = f"{self.state['baseDirectory']}{_sep}{name}"
+        for attempt in range(3):
+            _time.sleep(attempt * float(self.cache.get('zip_retry_seconds', 1.0)))
+            if _os.path.exists(src):
+                _shutil.copy(src, f"{self.state['outputDirectory']}{_sep}{name}")
+                break
+
+    def _get_learner_cls(self, learner_cls):
+        """``agg_engine`` x ``transport`` -> learner class; unknown engines use ``learner_cls``."""
+        engine = self.cache.get('agg_engine')
+        transport = self.cache.get('transport', Transport.FILE)
+        if transport in (Transport.NVLINK, Transport.NCCL):
+            from ...parallel import nvlink_learner as _nv
+            table = {AGG_Engine.dSGD: _nv.NvlinkLearner, AGG_Engine.powerSGD: _nv.NvlinkPowerSGDLearner,
+                     AGG_Engine.rankDAD: _nv.NvlinkDADLearner}
+            if engine in table:
+                return table[engine]
+        return _engine_learners().get(engine, learner_cls)
+
+    def __call__(self, *args, **kwargs):
+        try:
+            self.compute(*args, **kwargs)
+            return {'output': self.out}
+        except Exception:
+            _tback.print_exc()
+            raise Exception(self.out)

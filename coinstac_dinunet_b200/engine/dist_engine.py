@@ -1,0 +1,114 @@
+"""One-process-per-site round engine over ``torch.distributed`` (rank r == site ``local<r>``;
+rank 0 additionally hosts the aggregator).
+
+This is the B200 deployment shape: launched with ``torch.distributed.run`` (NCCL on GPUs, gloo on
+CPU), every rank owns one GPU and its node cache.  The JSON control plane travels through
+``gather_object`` / ``broadcast_object_list`` - tiny and, with the NVLink transport, touched once
+per epoch; the tensor data plane never goes through here (it is inside the fused kernel).  Files
+that still exist in the protocol (pre-trained weights broadcast, results zip, and the ``*.npy``
+payloads of the file transport) are shipped by rank 0 on the node-local filesystem exactly like
+the in-process emulator does.
+"""
+import os as _os
+import time as _time
+
+import torch as _torch
+import torch.distributed as _dist
+
+from .emulator import _clear_files, _copy_tree_flat, node_state, unwrap_spec
+
+
+def init_process_group(backend=None):
+    """Idempotent ``init_process_group`` from the torchrun environment (``127.0.0.1`` default)."""
+    if _dist.is_initialized():
+        return
+    _os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    _os.environ.setdefault('MASTER_PORT', '29512')
+    _os.environ.setdefault('RANK', '0')
+    _os.environ.setdefault('WORLD_SIZE', '1')
+    cuda = _torch.cuda.is_available()
+    backend = backend or ('nccl' if cuda else 'gloo')
+    kw = {}
+    if backend == 'nccl':
+        local = int(_os.environ.get('LOCAL_RANK', '0'))
+        _torch.cuda.set_device(local)
+        kw['device_id'] = _torch.device('cuda', local)
+    _dist.init_process_group(backend=backend, **kw)
+
+
+def _jsonish(obj):
+    """Make an output dict picklable/JSON-like (enum keys -> str, FrozenDict -> dict)."""
+    if isinstance(obj, dict):
+        return {str(k): _jsonish(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [_jsonish(v) for v in obj]
+    if isinstance(obj, str):
+        return str(obj)
+    return obj
+
+
+class DistEngine:
+    def __init__(self, work_dir, inputspec=None, clear_transfer=True, group=None):
+        init_process_group()
+        self.group = group
+        self.rank, self.world = _dist.get_rank(group), _dist.get_world_size(group)
+        self.work_dir = str(work_dir)
+        self.site_ids = [f'local{i}' for i in range(self.world)]
+        self.site = self.site_ids[self.rank]
+        self.clear_transfer = clear_transfer
+        self.state = node_state(self.work_dir, self.site)
+        self.cache = {}
+        spec = inputspec[self.rank] if isinstance(inputspec, (list, tuple)) else (inputspec or {})
+        self.input = unwrap_spec(spec)
+        self.remote_state = node_state(self.work_dir, 'remote') if self.rank == 0 else None
+        self.remote_cache = {} if self.rank == 0 else None
+        self.all_site_states = [node_state(self.work_dir, s) for s in self.site_ids] if self.rank == 0 else None
+        self.trace, self.round, self.timings = [], 0, []
+
+    def step(self, local_fn, remote_fn):
+        t0 = _time.time()
+        out = local_fn(self.site, self.cache, self.input, self.state)['output']
+        gathered = [None] * self.world if self.rank == 0 else None
+        _dist.gather_object(_jsonish(out), gathered, dst=0, group=self.group)  # doubles as file barrier
+        payload = [None]
+        if self.rank == 0:
+            for st in self.all_site_states:
+                src = st['transferDirectory']
+                _copy_tree_flat(src, _os.path.join(self.remote_state['baseDirectory'], st['clientId']))
+                if self.clear_transfer:
+                    _clear_files(src)
+            res = remote_fn(self.remote_cache, dict(zip(self.site_ids, gathered)), self.remote_state)
+            for st in self.all_site_states:
+                _copy_tree_flat(self.remote_state['transferDirectory'], st['baseDirectory'])
+            if self.clear_transfer:
+                _clear_files(self.remote_state['transferDirectory'])
+            payload = [(_jsonish(res['output']), bool(res.get('success')))]
+        _dist.broadcast_object_list(payload, src=0, group=self.group)
+        remote_out, success = payload[0]
+        self.input = dict(remote_out)
+        self.trace.append({'site': (str(out.get('phase')), str(out.get('mode'))),
+                           'remote': str(remote_out.get('phase'))})
+        self.timings.append(_time.time() - t0)
+        self.round += 1
+        return success
+
+    def run(self, local_fn, remote_fn, max_rounds=100000):
+        while self.round < max_rounds:
+            if self.step(local_fn, remote_fn):
+                return self.round
+        raise RuntimeError(f'engine did not converge within {max_rounds} rounds')
+
+    def run_nodes(self, trainer_cls, dataset_cls=None, datahandle_cls=None, local_kw=None, remote_kw=None,
+                  mp_pool=None, max_rounds=100000):
+        from ..data import COINNDataHandle
+        from ..distrib.nodes import COINNLocal, COINNRemote
+        local_kw, remote_kw = dict(local_kw or {}), dict(remote_kw or {})
+        dh = datahandle_cls or COINNDataHandle
+
+        def local_fn(site, cache, inp, state):
+            return COINNLocal(cache=cache, input=inp, state=state, **local_kw)(mp_pool, trainer_cls, dataset_cls, dh)
+
+        def remote_fn(cache, inp, state):
+            return COINNRemote(cache=cache, input=inp, state=state, **remote_kw)(mp_pool, trainer_cls)
+
+        return self.run(local_fn, remote_fn, max_rounds=max_rounds)
