@@ -188,6 +188,7 @@ class COINNLocal:
     def _computation_round(self, trainer, learner, dataset_cls):
         modes = list(learner.global_modes.values())
         if self.input.get('save_current_as_best'):
+            self._sync_optimizer_state()
             learner.trainer.save_checkpoint(file_path=self.cache['log_dir'] + _sep + self.cache['best_nn_state'])
 
         if self.input.get('update'):
@@ -212,8 +213,16 @@ class COINNLocal:
             self.out.update(**trainer.test_distributed(dataset_cls))
             self.out['mode'] = self.cache['frozen_args']['mode']
             self.out['phase'] = Phase.NEXT_RUN_WAITING
+            self._sync_optimizer_state()
             trainer.save_checkpoint(file_path=self.cache['log_dir'] + _sep + self.cache['latest_nn_state'])
             _utils.save_cache(self.cache, self.cache['log_dir'])
+
+    def _sync_optimizer_state(self):
+        """Sharded (two-shot / NVLS) optimizer moments are collected before a global checkpoint;
+        every site reaches these save points in the same round, so the collective is matched."""
+        arena = self.cache.get('_arena')
+        if arena is not None:
+            arena.gather_state()
 
     def _collect_results(self):
         """Final round: pick up the results zip broadcast by the aggregator (retry x3)."""

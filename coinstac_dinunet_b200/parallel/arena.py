@@ -1,0 +1,286 @@
+"""Flat parameter / gradient / optimizer-state arenas and the fused dSGD step.
+
+``DistArena`` re-homes the parameters of a model into one flat fp32 buffer (``p.data`` become
+views), pre-binds ``p.grad`` to views of one flat *symmetric* gradient buffer that autograd then
+accumulates into in place (this removes the reference's per-parameter D2H/H2D copies,
+tensorutils.py:44-47 / learner.py:25-26), and keeps Adam/SGD state in flat buffers.  One call
+``reduce_and_step()`` launches ``fused_reduce_opt.cu`` which averages the gradients of all sites
+over NVLink, applies the optimizer and re-zeroes the gradient buffer - the whole of the reference's
+``to_reduce -> COINNReducer.reduce -> step`` round trip.
+
+Variant choice per bucket (``variant='auto'``): one-shot below ``config.ONE_SHOT_MAX_BYTES``,
+otherwise NVLS when the allocation has a multicast alias, else two-shot.
+Backends: ``'nvlink'`` fused kernel (product) | ``'nccl'`` all-reduce + fused local step (the
+baseline the spec names) | ``'torch'`` all-reduce + torch optimizer (CPU/gloo, used by the tests).
+"""
+import ctypes as _C
+
+import torch as _torch
+import torch.distributed as _dist
+
+from .. import config as _conf
+from .symm import SymmetricBuffer, _rank, _world
+
+_ALIGN = 8          # elements; keeps every parameter 16-byte aligned in fp32 and in a bf16 shadow
+_VARIANTS = {'one_shot': 0, 'two_shot': 1, 'nvls': 2}
+_OPT_KINDS = {'adam': 0, 'adamw': 1, 'sgd': 2}
+
+
+def _round_up(n, a):
+    return (n + a - 1) // a * a
+
+
+def describe_optimizer(opt):
+    """Hyper-parameters of a torch optimizer that the fused kernel can reproduce, or None."""
+    if len(opt.param_groups) != 1:
+        return None
+    g = opt.param_groups[0]
+    if isinstance(opt, _torch.optim.AdamW) or isinstance(opt, _torch.optim.Adam):
+        if g.get('amsgrad') or g.get('maximize'):
+            return None
+        kind = 'adamw' if (isinstance(opt, _torch.optim.AdamW) or g.get('decoupled_weight_decay')) else 'adam'
+        return dict(kind=kind, lr=float(g['lr']), beta1=float(g['betas'][0]), beta2=float(g['betas'][1]),
+                    eps=float(g['eps']), weight_decay=float(g['weight_decay']), momentum=0.0, nesterov=0)
+    if isinstance(opt, _torch.optim.SGD):
+        if g.get('maximize') or g.get('dampening', 0) != 0:
+            return None
+        return dict(kind='sgd', lr=float(g['lr']), beta1=0.0, beta2=0.0, eps=0.0,
+                    weight_decay=float(g['weight_decay']), momentum=float(g['momentum']),
+                    nesterov=int(bool(g['nesterov'])))
+    return None
+
+
+class DistArena:
+    def __init__(self, model, optimizer, device=None, group=None, backend='auto', shadow_bf16=False,
+                 variant='auto', bucket_bytes=None):
+        self.model, self.optimizer, self.group = model, optimizer, group
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.device = _torch.device(device) if device is not None else self.params[0].device
+        self.world, self.rank = _world(group), _rank(group)
+        self.variant = variant
+        self.hyper = describe_optimizer(optimizer)
+
+        if backend == 'auto':
+            backend = 'nvlink' if self.device.type == 'cuda' else 'torch'
+        if backend in ('nvlink', 'nccl') and (self.device.type != 'cuda' or self.hyper is None):
+            backend = 'torch'
+        self.backend = backend
+
+        # ---- layout -------------------------------------------------------------------------
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += _round_up(p.numel(), _ALIGN)
+        self.numel = _round_up(max(off, _ALIGN), 4 * max(self.world, 1))
+        self.bucket_bytes = bucket_bytes
+
+        sym = backend == 'nvlink'
+        mk = (lambda n, dt: SymmetricBuffer(n, dt, self.device, group)) if sym else \
+            (lambda n, dt: _Local(n, dt, self.device))
+        self.grad_buf = mk(self.numel, _torch.float32)
+        self.param_buf = mk(self.numel, _torch.float32)
+        self.shadow_buf = mk(self.numel, _torch.bfloat16) if shadow_bf16 else None
+        self.flat_grad, self.flat_param = self.grad_buf.local, self.param_buf.local
+        self.m = _torch.zeros(self.numel, dtype=_torch.float32, device=self.device)
+        self.v = _torch.zeros(self.numel, dtype=_torch.float32, device=self.device)
+        self.step_count = _torch.zeros(1, dtype=_torch.int32, device=self.device)
+        self.steps_done = 0     # optimizer steps taken through this arena (host mirror of step_count)
+        self.host_step = 0      # Adam's `step` as torch.optim would report it
+
+        if backend in ('nvlink', 'nccl'):
+            from ..ops import native as _nat
+            self._nat = _nat
+            slots = _nat.lib().coinn_fused_flag_slots()
+            self.flags = mk(slots, _torch.int32)
+            self.epoch = _torch.zeros(_nat.lib().coinn_fused_max_blocks(), dtype=_torch.int32, device=self.device)
+            self.ticket = _torch.zeros(1, dtype=_torch.int32, device=self.device)
+            self._args_cache = {}
+
+        self._bind()
+        self.import_optimizer_state()
+
+    # ------------------------------------------------------------------------------ binding
+    def _bind(self):
+        """Move parameter storage into the arena and pre-bind ``.grad`` views."""
+        with _torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                n = p.numel()
+                view = self.flat_param[off:off + n].view(p.shape)
+                view.copy_(p.data.to(self.device, _torch.float32))
+                p.data = view
+                p.grad = self.flat_grad[off:off + n].view(p.shape)
+            if self.shadow_buf is not None:
+                self.shadow_buf.local.copy_(self.flat_param)
+        self._publish_state_views()
+        if self.world > 1 and self.grad_buf.__class__ is SymmetricBuffer:
+            _torch.cuda.synchronize(self.device)
+            self.grad_buf.barrier()
+
+    def shadow_view(self, p):
+        """bf16 view of parameter ``p`` in the shadow arena (native modules read this)."""
+        i = next(k for k, q in enumerate(self.params) if q is p)
+        off = self.offsets[i]
+        return self.shadow_buf.local[off:off + p.numel()].view(p.shape)
+
+    def rebind_grads(self):
+        """Re-attach ``p.grad`` to the arena (after ``optimizer.zero_grad(set_to_none=True)``)."""
+        for p, off in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + off * 4:
+                p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
+
+    def refresh_from_params(self):
+        """After a checkpoint load wrote new values through ``p.data``: nothing to copy (the views
+        ARE the arena) unless a loader replaced the tensors; then re-bind."""
+        with _torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                if p.data_ptr() != self.flat_param.data_ptr() + off * 4:
+                    self.flat_param[off:off + p.numel()].view(p.shape).copy_(p.data)
+                    p.data = self.flat_param[off:off + p.numel()].view(p.shape)
+            if self.shadow_buf is not None:
+                self.shadow_buf.local.copy_(self.flat_param)
+        self.rebind_grads()
+        self.import_optimizer_state()
+
+    # ------------------------------------------------------------------- optimizer state bridge
+    def _publish_state_views(self):
+        """Expose the arena through ``optimizer.state`` so ``state_dict()`` stays torch-compatible."""
+        if self.hyper is None or self.backend == 'torch':
+            return
+        for p, off in zip(self.params, self.offsets):
+            n = p.numel()
+            st = self.optimizer.state[p]
+            if self.hyper['kind'] == 'sgd':
+                st['momentum_buffer'] = self.m[off:off + n].view(p.shape)
+            else:
+                st['step'] = _torch.tensor(float(self.host_step))
+                st['exp_avg'] = self.m[off:off + n].view(p.shape)
+                st['exp_avg_sq'] = self.v[off:off + n].view(p.shape)
+
+    def import_optimizer_state(self):
+        """Copy existing torch optimizer state (e.g. from a loaded checkpoint) into the arena."""
+        if self.hyper is None or self.backend == 'torch':
+            return
+        step = 0
+        with _torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                st = self.optimizer.state.get(p, {})
+                n = p.numel()
+                for key, buf in (('exp_avg', self.m), ('exp_avg_sq', self.v), ('momentum_buffer', self.m)):
+                    t = st.get(key)
+                    if t is not None and t.data_ptr() != buf.data_ptr() + off * 4:
+                        buf[off:off + n].view(p.shape).copy_(t.to(self.device, _torch.float32))
+                if 'step' in st:
+                    step = max(step, int(float(st['step'])))
+        if step:
+            self.step_count.fill_(step)
+            self.host_step = step
+        self._publish_state_views()
+
+    def gather_state(self):
+        """Two-shot/NVLS keep optimizer moments sharded (rank r owns shard r).  Before a checkpoint
+        every rank collects the other shards so the saved state is complete."""
+        if self.world == 1 or self.backend != 'nvlink':
+            self._publish_state_views()
+            return
+        shard = self.numel // self.world
+        for buf in (self.m, self.v):
+            parts = list(buf.view(self.world, shard).unbind(0))
+            _dist.all_gather(parts, parts[self.rank].clone(), group=self.group)
+        self._publish_state_views()
+
+    # ------------------------------------------------------------------------------- the step
+    def _pick_variant(self, nbytes):
+        v = self.variant
+        if v == 'auto':
+            if self.world == 1 or nbytes <= _conf.ONE_SHOT_MAX_BYTES:
+                v = 'one_shot'
+            elif self.grad_buf.multicast_ptr and self.param_buf.multicast_ptr:
+                v = 'nvls'
+            else:
+                v = 'two_shot'
+        if v == 'nvls' and not (self.grad_buf.multicast_ptr and self.param_buf.multicast_ptr):
+            v = 'two_shot'
+        return v
+
+    def _fused_args(self, offset, numel, variant, world, grad_scale, zero_grads, bump):
+        nat, h = self._nat, self.hyper
+        key = (offset, numel, variant, world, zero_grads, bump)
+        a = self._args_cache.get(key)
+        if a is None:
+            a = nat.FusedArgs()
+            for r in range(world):
+                a.grad_ptrs[r] = self.grad_buf.peer_ptrs[r] if world > 1 else self.flat_grad.data_ptr()
+                a.param_ptrs[r] = self.param_buf.peer_ptrs[r] if world > 1 else self.flat_param.data_ptr()
+                a.flag_ptrs[r] = self.flags.peer_ptrs[r] if world > 1 else self.flags.local.data_ptr()
+                if self.shadow_buf is not None:
+                    a.shadow_ptrs[r] = self.shadow_buf.peer_ptrs[r] if world > 1 else self.shadow_buf.local.data_ptr()
+            if world > 1:
+                a.grad_mc = self.grad_buf.multicast_ptr or None
+                a.param_mc = self.param_buf.multicast_ptr or None
+                a.shadow_mc = (self.shadow_buf.multicast_ptr or None) if self.shadow_buf is not None else None
+            a.m, a.v = self.m.data_ptr(), self.v.data_ptr()
+            a.epoch, a.step, a.ticket = self.epoch.data_ptr(), self.step_count.data_ptr(), self.ticket.data_ptr()
+            a.offset, a.numel = offset, numel
+            a.rank, a.world = (self.rank if world > 1 else 0), world
+            a.variant, a.opt_kind, a.grad_dtype = _VARIANTS[variant], _OPT_KINDS[h['kind']], 0
+            a.zero_grads, a.bump_step, a.nesterov = int(zero_grads), int(bump), h['nesterov']
+            self._args_cache[key] = a
+        g = self.optimizer.param_groups[0]   # live values: lr schedulers keep working in eager mode
+        a.lr = float(g['lr'])
+        a.beta1, a.beta2, a.eps = h['beta1'], h['beta2'], h['eps']
+        a.weight_decay, a.momentum, a.grad_scale = float(g.get('weight_decay', 0.0)), h['momentum'], grad_scale
+        return a
+
+    def _launch(self, world, grad_scale, zero_grads=True):
+        nat = self._nat
+        variant = self._pick_variant(self.numel * 4) if world > 1 else 'one_shot'
+        a = self._fused_args(0, self.numel, variant, world, grad_scale, zero_grads, True)
+        nat.check(nat.lib().coinn_fused_reduce_opt(_C.byref(a), 0, nat.stream_ptr(self.device)),
+                  'coinn_fused_reduce_opt')
+        from .. import ops as _ops
+        _ops._count_launch()
+        return variant
+
+    def reduce_and_step(self, zero_grads=True):
+        """Average gradients over all sites and apply the optimizer.  Returns the variant used."""
+        self.steps_done += 1
+        self.host_step += 1
+        if self.backend == 'nvlink':
+            return self._launch(self.world, 1.0 / self.world, zero_grads)
+        if self.backend == 'nccl':
+            if self.world > 1:
+                _dist.all_reduce(self.flat_grad, op=_dist.ReduceOp.SUM, group=self.group)
+            self._launch(1, 1.0 / self.world, zero_grads)
+            return 'nccl'
+        # ---- torch fallback (CPU / exotic optimizers) ------------------------------------------
+        if self.world > 1:
+            _dist.all_reduce(self.flat_grad, op=_dist.ReduceOp.SUM, group=self.group)
+            self.flat_grad.div_(self.world)
+        self.optimizer.step()
+        if zero_grads:
+            self.flat_grad.zero_()
+        return 'torch'
+
+    def local_step(self, zero_grads=True):
+        """Optimizer step on the local gradients only (pre-training / single site)."""
+        self.steps_done += 1
+        self.host_step += 1
+        if self.backend in ('nvlink', 'nccl'):
+            self._launch(1, 1.0, zero_grads)
+        else:
+            self.optimizer.step()
+            if zero_grads:
+                self.flat_grad.zero_()
+
+
+class _Local:
+    """Same surface as SymmetricBuffer for buffers that never leave the device."""
+
+    def __init__(self, numel, dtype, device):
+        self.local = _torch.zeros(int(numel), dtype=dtype, device=device)
+        self.peer_ptrs = [self.local.data_ptr()]
+        self.multicast_ptr = 0
+        self.handle = None
+
+    def barrier(self):
+        pass

@@ -1,0 +1,233 @@
+"""Learners whose per-step gradient exchange happens inside the fused sm_100a kernel.
+
+``NvlinkLearner`` keeps the COINNLearner surface (``step`` / ``backward`` / ``to_reduce``) but one
+``to_reduce()`` call runs *a whole local epoch*: every step is ``backward`` (``local_iterations``
+micro-batches, gradients accumulate straight into the symmetric arena) followed by
+``arena.reduce_and_step()`` - gradient mean over all sites + optimizer update in one kernel, no
+NCCL, no host copy, no JSON.  The JSON control plane is only touched when the epoch is over
+(``mode = validation_waiting``), i.e. once per epoch instead of once per step.
+
+Epoch length: all sites must launch the same number of fused steps, so the number of steps per
+round is ``max`` over sites of their local step count (one tiny all-reduce per epoch).  Sites with
+less data wrap around and keep contributing - the reference's "lagging sites re-shuffle and
+continue until everyone is waiting" rule (local.py:232-238), decided up-front instead of round
+by round.
+
+The same code runs on CPU with the gloo backend (``DistArena`` falls back to all-reduce +
+``optimizer.step``), which is how the host-side logic is tested without a GPU.
+"""
+import torch as _torch
+import torch.distributed as _dist
+
+from ..config.keys import Mode, Transport
+from ..distrib.learner import COINNLearner
+from .arena import DistArena
+
+
+def _dist_on():
+    return _dist.is_available() and _dist.is_initialized()
+
+
+class NvlinkLearner(COINNLearner):
+    @property
+    def arena(self):
+        """The flat arenas + fused optimizer of this site; built on first use (the learner object
+        is re-created every round, also in phases where no model exists yet)."""
+        arena = self.cache.get('_arena')
+        if arena is None or arena.model is not self.model or arena.optimizer is not self.optim:
+            transport = self.cache.get('transport', Transport.NVLINK)
+            backend = {'nvlink': 'nvlink', 'nccl': 'nccl'}.get(str(transport), 'auto')
+            if self.device.type != 'cuda':
+                backend = 'torch'
+            arena = DistArena(self.model, self.optim, device=self.device, backend=backend,
+                              variant=self.cache.get('reduce_variant', 'auto'),
+                              shadow_bf16=bool(self.cache.get('shadow_bf16', False)))
+            self.cache['_arena'] = arena
+        return arena
+
+    # the update is fused into to_reduce(); nothing left to apply when the remote says `update`
+    def step(self) -> dict:
+        return {}
+
+    def _steps_this_round(self):
+        """max over sites of local steps per epoch (so every site launches the same kernels)."""
+        fixed = self.cache.get('steps_per_round')
+        if fixed:
+            return int(fixed)
+        ds = self.trainer.data_handle.dataset.get('train')
+        bs = int(self.cache['batch_size']) * int(self.cache.get('local_iterations', 1))
+        mine = -(-len(ds) // bs) if ds is not None and len(ds) else 1
+        if _dist_on() and _dist.get_world_size() > 1:
+            t = _torch.tensor([mine], dtype=_torch.int64, device=self.device if self.device.type == 'cuda' else 'cpu')
+            _dist.all_reduce(t, op=_dist.ReduceOp.MAX)
+            mine = int(t.item())
+        return max(mine, 1)
+
+    def backward(self):
+        """Micro-batches accumulate into the arena (it is zeroed by the fused kernel's tail)."""
+        out, its = {}, []
+        self.model.train()
+        self.arena.rebind_grads()
+        for _ in range(self.cache.get('local_iterations', 1)):
+            batch, flags = self.trainer.data_handle.next_iter()
+            it = self.trainer.iteration(batch)
+            it['loss'].backward()
+            its.append(it)
+            out.update(**flags)
+        return its, out
+
+    def to_reduce(self):
+        its, out = [], {}
+        for _ in range(self._steps_this_round()):
+            step_its, flags = self.backward()
+            self.arena.reduce_and_step()
+            its.extend(step_its)
+        # the round IS the epoch: report it finished regardless of where the local cursor is
+        self.cache['cursor'] = 0
+        out['mode'] = Mode.VALIDATION_WAITING
+        out['fused_steps'] = self.arena.steps_done
+        return self.trainer.reduce_iteration(its), out
+
+
+class NvlinkPowerSGDLearner(NvlinkLearner):
+    """PowerSGD over the device collectives (P/Q factors all-reduced instead of shipped as files).
+    Math as in ``distrib.powersgd`` (rank-r, error feedback, warm start); the two reductions per
+    step are ``torch.distributed`` all-reduces of the small factor buffers."""
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        from ..distrib.powersgd import PowerSGDState
+        c = self.cache
+        self.rank_r = c.setdefault('matrix_approximation_rank', 1)
+        self.start_iter = c.setdefault('start_powerSGD_iter', 10)
+        self.error_feedback = c.setdefault('use_error_feedback', True)
+        self.warm_start = c.setdefault('warm_start', True)
+        self.seed = c.get('seed') or 0
+        self.st = c.setdefault('powerSGD_state', PowerSGDState())
+
+    def _allreduce_mean(self, tensors):
+        if not tensors:
+            return
+        flat = _torch.cat([t.reshape(-1) for t in tensors])
+        if _dist_on() and _dist.get_world_size() > 1:
+            _dist.all_reduce(flat, op=_dist.ReduceOp.SUM)
+            flat /= _dist.get_world_size()
+        off = 0
+        for t in tensors:
+            t.copy_(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
+
+    def _compressed_step(self):
+        from ..distrib.powersgd import _native_orthogonalize, _as_matrix
+        st = self.st
+        mats, low = [], []
+        for key, p in self.model.named_parameters():
+            if p.grad is None:
+                continue
+            (low if p.dim() <= 1 else mats).append((key, p))
+        Ps = []
+        for key, p in mats:
+            M = _as_matrix(p.grad.detach().float().clone())
+            if self.error_feedback and key in st.error_dict:
+                M += st.error_dict[key]
+            if not self.warm_start or key not in st.q_memory_dict:
+                gen = _torch.Generator(device='cpu').manual_seed(int(self.seed) + int(st.iter))
+                st.q_memory_dict[key] = _torch.randn(M.shape[1], self.rank_r, generator=gen).to(M.device)
+            _native_orthogonalize(st.q_memory_dict[key])
+            st.high_rank_tensors[key] = M
+            st.p_memory_dict[key] = M @ st.q_memory_dict[key]
+            Ps.append(st.p_memory_dict[key])
+        self._allreduce_mean(Ps)
+        Qs = []
+        for key, p in mats:
+            _native_orthogonalize(st.p_memory_dict[key])
+            st.q_memory_dict[key] = st.high_rank_tensors[key].t() @ st.p_memory_dict[key]
+            Qs.append(st.q_memory_dict[key])
+        self._allreduce_mean(Qs + [p.grad for _, p in low])
+        for key, p in mats:
+            approx = st.p_memory_dict[key] @ st.q_memory_dict[key].t()
+            if self.error_feedback:
+                st.error_dict[key] = st.high_rank_tensors[key] - approx
+            p.grad.copy_(approx.view_as(p.grad))
+        st.high_rank_tensors.clear()
+        self.arena.local_step()
+
+    def to_reduce(self):
+        its, out = [], {}
+        for _ in range(self._steps_this_round()):
+            step_its, _ = self.backward()
+            if self.st.iter < self.start_iter:
+                self.arena.reduce_and_step()
+            else:
+                self._compressed_step()
+            self.st.iter += 1
+            its.extend(step_its)
+        self.cache['cursor'] = 0
+        out['mode'] = Mode.VALIDATION_WAITING
+        return self.trainer.reduce_iteration(its), out
+
+
+class NvlinkDADLearner(NvlinkLearner):
+    """rankDAD over device collectives: per-layer (delta, activation) factors are all-gathered,
+    concatenated along the rank axis and re-compressed on every site (deterministically, so the
+    replicas agree), then turned back into dense gradients for the fused local step."""
+
+    def __init__(self, **kw):
+        from ..distrib.rankdad.spi import DADParallel
+        COINNLearner.__init__(self, **kw)
+        for key in list(self.trainer.nn):
+            if not isinstance(self.trainer.nn[key], DADParallel):
+                self.trainer.nn[key] = DADParallel(self.trainer.nn[key], cache=self.cache, input=self.input,
+                                                   state=self.state, device=self.trainer.device['gpu'],
+                                                   dtype=self.dtype)
+        super().__init__(**kw)
+
+    def _dad_step(self):
+        from ..distrib.rankdad.spi import power_iteration_BC
+        wrapper = self.model
+        world = _dist.get_world_size() if _dist_on() else 1
+        rank_r, iters, tol = wrapper.rank, wrapper.num_pow_iters, wrapper.dad_tol
+        for name, m in wrapper.dad_layers(reverse=True):
+            delta, act = wrapper._factors(name, m)                # [out,k], [in(+1),k]
+            if world > 1:
+                ds = [_torch.empty_like(delta) for _ in range(world)]
+                as_ = [_torch.empty_like(act) for _ in range(world)]
+                _dist.all_gather(ds, delta.contiguous())
+                _dist.all_gather(as_, act.contiguous())
+                delta, act = _torch.cat(ds, 1), _torch.cat(as_, 1)
+                if delta.shape[1] > rank_r and self.cache.get('dad_recompress', True):
+                    delta, act = power_iteration_BC(delta, act, rank_r, iters, tol)
+            if self.cache.get('dad_mean'):
+                delta = delta / world
+            full = delta @ act.t()
+            if getattr(m, 'bias', None) is not None and act.shape[0] == m.weight.shape[1] + 1:
+                m.weight.grad.copy_(full[:, :-1])
+                m.bias.grad.copy_(full[:, -1])
+            else:
+                m.weight.grad.copy_(full)
+        plain = [p.grad for p in wrapper.plain_parameters() if p.grad is not None]
+        if plain and world > 1:
+            flat = _torch.cat([g.reshape(-1) for g in plain])
+            _dist.all_reduce(flat)
+            if self.cache.get('dad_mean'):
+                flat /= world
+            off = 0
+            for g in plain:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        self.arena.local_step()
+
+    def to_reduce(self):
+        its, out = [], {}
+        saved = self.cache.get('local_iterations', 1)
+        self.cache['local_iterations'] = 1          # rankDAD cannot accumulate gradients
+        try:
+            for _ in range(self._steps_this_round()):
+                step_its, _ = self.backward()
+                self._dad_step()
+                its.extend(step_its)
+        finally:
+            self.cache['local_iterations'] = saved
+        self.cache['cursor'] = 0
+        out['mode'] = Mode.VALIDATION_WAITING
+        return self.trainer.reduce_iteration(its), out

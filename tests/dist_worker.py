@@ -1,0 +1,57 @@
+"""Worker launched by torch.distributed.run from the tests (gloo on CPU, nccl on GPUs).
+
+usage: dist_worker.py <scenario> <work_dir> [key=value ...]
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def scenario_protocol(work, opts):
+    """Full k-fold dSGD run with one process per site through DistEngine + NvlinkLearner."""
+    from coinstac_dinunet_b200.engine import DistEngine
+    from coinstac_dinunet_b200.models import FSVDataset, FSVTrainer, write_synthetic_site
+    spec = dict(task_id='fsv', mode='train', data_dir='data', labels_file='labels.json', input_size=66, num_class=2,
+                batch_size=4, epochs=2, num_folds=None, split_ratio=[0.6, 0.2, 0.2], learning_rate=1e-2, seed=7,
+                transport=opts.get('transport', 'nvlink'), agg_engine=opts.get('agg_engine', 'dSGD'),
+                start_powerSGD_iter=2, matrix_approximation_rank=2,
+                gpus=[int(os.environ.get('LOCAL_RANK', 0))] if torch.cuda.is_available() else None)
+    eng = DistEngine(work, inputspec=spec)
+    sizes = [24, 18, 30, 12, 20, 16, 28, 22]
+    write_synthetic_site(eng.state['baseDirectory'], sizes[eng.rank % len(sizes)], (66,), seed=eng.rank)
+    rounds = eng.run_nodes(FSVTrainer, FSVDataset, max_rounds=500)
+    model = eng.cache['nn']['fs_net']
+    flat = torch.cat([p.detach().float().reshape(-1).cpu() for p in model.parameters()])
+    gathered = [None] * eng.world
+    dist.all_gather_object(gathered, flat)
+    if eng.rank == 0:
+        same = all(torch.equal(gathered[0], g) for g in gathered[1:])
+        csv = os.path.join(eng.remote_state['outputDirectory'], 'fsv', 'global_test_metrics.csv')
+        res = {'rounds': rounds, 'replicas_identical': bool(same), 'csv': os.path.exists(csv),
+               'backend': eng.cache['_arena'].backend, 'fused_steps': eng.cache['_arena'].steps_done,
+               'trace': [t['remote'] for t in eng.trace]}
+        with open(os.path.join(work, 'result.json'), 'w') as fp:
+            json.dump(res, fp)
+
+
+SCENARIOS = {'protocol': scenario_protocol}
+
+if __name__ == '__main__':
+    name, work = sys.argv[1], sys.argv[2]
+    opts = dict(kv.split('=', 1) for kv in sys.argv[3:])
+    from coinstac_dinunet_b200.engine import init_process_group
+    init_process_group()
+    try:
+        from tests import dist_scenarios_gpu  # noqa: F401  (registers GPU scenarios when present)
+        SCENARIOS.update(dist_scenarios_gpu.SCENARIOS)
+    except Exception:
+        pass
+    SCENARIOS[name](work, opts)
+    dist.barrier()
+    dist.destroy_process_group()

@@ -1,0 +1,30 @@
+"""Multi-process (gloo, world_size 2) tests of the one-process-per-site engine and of the host
+logic of the NVLink learners (the data plane falls back to all-reduce + optimizer.step on CPU)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_workers(scenario, work, nproc=2, port=29611, extra=(), timeout=600, env=None):
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={nproc}',
+           '--master-addr', '127.0.0.1', '--master-port', str(port),
+           os.path.join(ROOT, 'tests', 'dist_worker.py'), scenario, str(work), *extra]
+    e = dict(os.environ)
+    e.update(env or {})
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=e)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    with open(os.path.join(work, 'result.json')) as fp:
+        return json.load(fp)
+
+
+@pytest.mark.parametrize('engine,port', [('dSGD', 29611), ('powerSGD', 29612), ('rankDAD', 29613)])
+def test_dist_engine_two_sites(tmp_path, engine, port):
+    res = run_workers('protocol', tmp_path, port=port, extra=[f'agg_engine={engine}'])
+    assert res['csv'] and res['trace'][-2] == 'success'
+    assert res['replicas_identical']
+    assert res['backend'] == 'torch' and res['fused_steps'] > 0
