@@ -34,10 +34,19 @@ class ClassificationTrainer(COINNTrainer):
             x = x.float()
         return x, y
 
+    def _forward(self, model, x):
+        """bf16/fp16 compute for stock ``nn.Module``s goes through autocast; native modules (which
+        carry their own low-precision shadows) are called directly."""
+        dt = self.compute_dtype
+        if dt in (_torch.bfloat16, _torch.float16) and x.is_cuda and not getattr(model, 'is_native', False):
+            with _torch.autocast('cuda', dtype=dt):
+                return model(x)
+        return model(x)
+
     def iteration(self, batch):
         x, y = self._inputs(batch)
         model = self.nn[next(iter(self.nn))]
-        logits = model(x)
+        logits = self._forward(model, x)
         loss, pred = _ops.softmax_nll(logits, y)
         avg, met = self.new_averages(), self.new_metrics()
         avg.add(loss.detach(), len(y))
@@ -46,6 +55,30 @@ class ClassificationTrainer(COINNTrainer):
         else:
             met.add(pred, y)
         return {'loss': loss, 'averages': avg, 'metrics': met, 'prediction': pred}
+
+
+def pinned_collate(batch):
+    """Collate for in-memory datasets: when the samples of a batch are consecutive views of one
+    (pinned) host tensor the batch is a zero-copy slice of it - the H2D DMA then reads pinned
+    memory directly; otherwise fall back to stacking."""
+    batch = [b for b in batch if b]
+    first = batch[0]
+    out = {}
+    for key in first:
+        vals = [b[key] for b in batch]
+        v0 = vals[0]
+        if isinstance(v0, _torch.Tensor) and v0.dim() > 0 and v0.is_contiguous():
+            step = v0.numel() * v0.element_size()
+            base = getattr(v0, '_base', None)
+            consecutive = base is not None and all(
+                getattr(v, '_base', None) is base and v.data_ptr() == v0.data_ptr() + i * step
+                for i, v in enumerate(vals))
+            if consecutive:
+                start = (v0.data_ptr() - base.data_ptr()) // step
+                out[key] = base[start:start + len(vals)]
+                continue
+        out[key] = _torch.stack(vals) if isinstance(v0, _torch.Tensor) else _torch.as_tensor(vals)
+    return out
 
 
 class ArrayFileDataset(COINNDataset):
@@ -107,13 +140,25 @@ class InMemorySynthetic(COINNDataset):
         g = _torch.Generator().manual_seed(self.seed)
         n = len(self.indices)
         self._y = _torch.randint(0, self.num_class, (n,), generator=g)
-        x = _torch.randn((n, *self.shape), generator=g)
-        x += (self._y.float() * 2 - 1).view(-1, *([1] * len(self.shape))) * 0.5
-        self._x = x.to(self.dtype)
-        if self.pin and _torch.cuda.is_available():
+        distinct = min(n, int(self.cache.get('synthetic_distinct', n)) if self.cache else n)
+        x = _torch.randn((distinct, *self.shape), generator=g)
+        x += (self._y[:distinct].float() * 2 - 1).view(-1, *([1] * len(self.shape))) * 0.5
+        self._distinct = distinct   # samples index the pool modulo `distinct` (bounded host memory)
+        self._y = self._y[:distinct].contiguous()
+        self._x = x.to(self.dtype).contiguous()
+        if self._x._base is not None:
+            self._x = self._x.clone()
+        dev = self.cache.get('synthetic_device') if self.cache else None
+        if dev:
+            self._x, self._y = self._x.to(dev), self._y.to(dev)
+        elif self.pin and _torch.cuda.is_available():
             self._x, self._y = self._x.pin_memory(), self._y.pin_memory()
+
+    def load_index(self, file):
+        self.indices.append([file])
 
     def __getitem__(self, ix):
         if self._x is None:
             self._materialise()
-        return {'inputs': self._x[ix], 'labels': self._y[ix]}
+        j = ix % self._distinct
+        return {'inputs': self._x[j], 'labels': self._y[j]}

@@ -111,7 +111,6 @@ class DistArena:
                 p.grad = self.flat_grad[off:off + n].view(p.shape)
             if self.shadow_buf is not None:
                 self.shadow_buf.local.copy_(self.flat_param)
-        self._publish_state_views()
         if self.world > 1 and self.grad_buf.__class__ is SymmetricBuffer:
             _torch.cuda.synchronize(self.device)
             self.grad_buf.barrier()

@@ -81,6 +81,8 @@ class NvlinkLearner(COINNLearner):
         for _ in range(self._steps_this_round()):
             step_its, flags = self.backward()
             self.arena.reduce_and_step()
+            if self.cache.get('readback_per_step'):      # end-to-end mode: the caller wants the loss now
+                self.cache['last_loss'] = float(step_its[-1]['loss'].detach())
             its.extend(step_its)
         # the round IS the epoch: report it finished regardless of where the local cursor is
         self.cache['cursor'] = 0

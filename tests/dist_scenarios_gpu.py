@@ -1,0 +1,56 @@
+"""GPU scenarios for tests/dist_worker.py (multi-GPU, launched through torch.distributed.run)."""
+import json
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+
+def scenario_fused(work, opts):
+    """fused_reduce_opt.cu across S GPUs vs torch.optim.Adam on the exactly averaged gradient;
+    all variants, odd sizes, several steps, random per-rank delays, replica bit-equality."""
+    from coinstac_dinunet_b200.parallel.arena import DistArena
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    results = []
+    for variant in ('one_shot', 'two_shot', 'nvls'):
+        for width in (3, 64, 1000, 2049):
+            torch.manual_seed(42)                                   # identical init on all ranks
+            mk = lambda: torch.nn.Sequential(torch.nn.Linear(width, 17), torch.nn.Tanh(), torch.nn.Linear(17, width)).to(dev)
+            ours, ref = mk(), mk()
+            ref.load_state_dict(ours.state_dict())
+            o_opt, r_opt = torch.optim.Adam(ours.parameters(), lr=1e-2), torch.optim.Adam(ref.parameters(), lr=1e-2)
+            arena = DistArena(ours, o_opt, device=dev, backend='nvlink', variant=variant)
+            used = None
+            for step in range(4):
+                g = torch.Generator(device='cpu').manual_seed(1000 * step + rank)
+                x = torch.randn(8, width, generator=g).to(dev)
+                ours(x).square().mean().backward()
+                ref(x).square().mean().backward()
+                flat = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+                parts = [torch.empty_like(flat) for _ in range(world)]
+                dist.all_gather(parts, flat)
+                mean = torch.stack(parts).sum(0) / world            # fixed rank order, like the kernel
+                off = 0
+                for p in ref.parameters():
+                    p.grad.copy_(mean[off:off + p.numel()].view_as(p)); off += p.numel()
+                r_opt.step(); r_opt.zero_grad()
+                if (step + rank) % 2:
+                    time.sleep(0.01 * rank)                         # skew the ranks: barriers must hold
+                used = arena.reduce_and_step()
+            torch.cuda.synchronize()
+            err = max(float((a - b).abs().max()) for a, b in zip(ours.parameters(), ref.parameters()))
+            mine = arena.flat_param.clone()
+            allp = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allp, mine)
+            identical = all(torch.equal(allp[0], q) for q in allp[1:])
+            zeroed = float(arena.flat_grad.abs().max()) == 0.0
+            results.append({'variant': variant, 'used': used, 'width': width, 'err': err,
+                            'identical': identical, 'zeroed': zeroed})
+    if rank == 0:
+        with open(os.path.join(work, 'result.json'), 'w') as fp:
+            json.dump({'results': results, 'world': world}, fp)
+
+
+SCENARIOS = {'fused': scenario_fused}

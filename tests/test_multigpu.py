@@ -1,0 +1,26 @@
+"""Cross-GPU correctness of the fused NVLink kernels and of the full protocol on >= 2 GPUs."""
+import pytest
+import torch
+
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from test_dist_cpu import run_workers  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _n():
+    return min(torch.cuda.device_count(), 8)
+
+
+def test_fused_reduce_all_variants(tmp_path):
+    res = run_workers('fused', tmp_path, nproc=_n(), port=29701)
+    for r in res['results']:
+        assert r['identical'], r
+        assert r['zeroed'], r
+        assert r['err'] < 5e-6, r
+
+
+def test_protocol_over_nvlink(tmp_path):
+    res = run_workers('protocol', tmp_path, nproc=_n(), port=29702, extra=['transport=nvlink'])
+    assert res['backend'] == 'nvlink' and res['replicas_identical'] and res['csv']
