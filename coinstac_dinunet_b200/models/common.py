@@ -28,7 +28,10 @@ class ClassificationTrainer(COINNTrainer):
         x = batch[self.input_key].to(dev, non_blocking=True)
         y = batch[self.label_key].to(dev, non_blocking=True).long()
         dt = self.compute_dtype
-        if dt is not None and x.dtype != dt and x.is_floating_point() and dev.type == 'cuda':
+        native = getattr(self.nn[next(iter(self.nn))], 'is_native', False)
+        if native and x.is_floating_point():
+            pass                                         # native kernels read fp32/bf16 inputs directly
+        elif dt is not None and x.dtype != dt and x.is_floating_point() and dev.type == 'cuda':
             x = x.to(dt)
         elif not x.is_floating_point() or (dev.type == 'cpu' and x.dtype != _torch.float32):
             x = x.float()

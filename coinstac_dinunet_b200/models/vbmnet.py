@@ -38,9 +38,16 @@ class ConvBlock(_nn.Module):
 
 
 class VBMNet(_nn.Module):
+    """``native=True`` routes CUDA inputs through the hand-written sm_100a kernels (fused
+    conv+BN+ReLU+pool blocks in channels-last bf16, tcgen05 GEMMs for the head) using the very same
+    parameters/buffers - ``state_dict`` and optimizer layouts are identical in both modes."""
+
     def __init__(self, in_ch=1, num_class=2, channels=VBM_CHANNELS, head=VBM_HEAD,
-                 input_shape=VBM_INPUT_SHAPE[1:]):
+                 input_shape=VBM_INPUT_SHAPE[1:], native=False, conv_backend='auto'):
         super().__init__()
+        self.native = bool(native) and in_ch == 1 and channels[0] == 16 and \
+            all(c % 8 == 0 and c <= 256 and 256 % (c // 8) == 0 for c in channels)
+        self.conv_backend = conv_backend
         chans = [in_ch, *channels]
         self.blocks = _nn.Sequential(*[ConvBlock(a, b) for a, b in zip(chans[:-1], chans[1:])])
         d, h, w = _pooled(input_shape, len(channels))
@@ -52,11 +59,36 @@ class VBMNet(_nn.Module):
         self.head = _nn.Sequential(*fc)
         self.classifier = _nn.Linear(dims[-1], num_class)
 
+    @property
+    def is_native(self):
+        return self.native
+
     def forward(self, x):
+        if self.native and x.is_cuda:
+            return self._forward_native(x)
         if x.dim() == 4:
             x = x.unsqueeze(1)
         z = self.blocks(x)
         return self.classifier(self.head(z.flatten(1)))
+
+    def _forward_native(self, x):
+        from ..ops.linear import LinearFn
+        from ..ops.vbm import ConvBnReluPoolFn
+        h = x[:, 0] if x.dim() == 5 else x                     # [N, D, H, W]; C_in == 1
+        if h.dtype not in (_torch.float32, _torch.bfloat16):
+            h = h.float()
+        for blk in self.blocks:
+            bn = blk.bn
+            h = ConvBnReluPoolFn.apply(h, blk.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                       bn.eps, bn.momentum if bn.momentum is not None else 0.1, self.training,
+                                       self.conv_backend)
+            if self.training and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        z = h.permute(0, 4, 1, 2, 3).reshape(h.shape[0], -1)    # NCDHW flatten order == the torch path
+        for layer in self.head:
+            if isinstance(layer, _nn.Linear):
+                z = LinearFn.apply(z, layer.weight, layer.bias, True)
+        return LinearFn.apply(z, self.classifier.weight, self.classifier.bias, False).float()
 
 
 class VBMDataset(ArrayFileDataset):
@@ -74,4 +106,6 @@ class VBMTrainer(ClassificationTrainer):
         shape = tuple(self.cache.get('input_shape', VBM_INPUT_SHAPE))
         self.nn['vbm_net'] = VBMNet(in_ch=shape[0], num_class=self.cache.get('num_class', 2),
                                     channels=tuple(self.cache.get('channels', VBM_CHANNELS)),
-                                    head=tuple(self.cache.get('head', VBM_HEAD)), input_shape=shape[1:])
+                                    head=tuple(self.cache.get('head', VBM_HEAD)), input_shape=shape[1:],
+                                    native=bool(self.cache.get('native_ops', False)),
+                                    conv_backend=self.cache.get('conv_backend', 'auto'))

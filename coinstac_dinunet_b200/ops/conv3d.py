@@ -1,0 +1,80 @@
+"""Conv3d (k3, p1, s1) on the tcgen05 implicit-GEMM kernel (``csrc/conv3d_tcgen05.cu``).
+
+Weight layouts fed to the kernel (bf16, K padded to a multiple of 64 with zeros):
+    fprop   Wk[co, tap*Cin + ci]   = W[co, ci, kd, kh, kw]
+    dgrad   Wd[ci, tap'*Cout + co] = W[co, ci, 2-kd', 2-kh', 2-kw']      (dx = conv(dy, Wd))
+"""
+import torch as _torch
+
+from . import native as _nat
+
+BF16 = _torch.bfloat16
+_SUPPORTED = {(16, 32), (32, 64), (64, 128), (128, 256), (32, 16), (64, 32), (128, 64), (256, 128),
+              (16, 16), (32, 32), (64, 64), (128, 128)}
+
+
+def supported(cin, cout):
+    return (cin, cout) in _SUPPORTED
+
+
+def _bump(n=1):
+    from . import _count_launch
+    _count_launch(n)
+
+
+def _pad_k(w2d):
+    k = w2d.shape[1]
+    kpad = (k + 63) // 64 * 64
+    if kpad != k:
+        w2d = _torch.nn.functional.pad(w2d, (0, kpad - k))
+    return w2d.contiguous(), kpad
+
+
+def pack_fprop_weight(weight):
+    cout, cin = weight.shape[:2]
+    return _pad_k(weight.detach().permute(0, 2, 3, 4, 1).reshape(cout, 27 * cin).to(BF16))
+
+
+def pack_dgrad_weight(weight):
+    cout, cin = weight.shape[:2]
+    return _pad_k(weight.detach().flip(2, 3, 4).permute(1, 2, 3, 4, 0).reshape(cin, 27 * cout).to(BF16))
+
+
+def _igemm(x, wk, kpad, cout):
+    N, D, H, W, cin = x.shape
+    y = _torch.empty((N, D, H, W, cout), dtype=BF16, device=x.device)
+    code = _nat.lib().coinn_conv3d_igemm(x.data_ptr(), wk.data_ptr(), y.data_ptr(), N, D, H, W, cin, cout, kpad,
+                                         _nat.stream_ptr(x.device))
+    _nat.check(code, f'coinn_conv3d_igemm({cin}->{cout})')
+    _bump()
+    return y
+
+
+def conv3d_igemm_fwd(x, weight):
+    """x: [N,D,H,W,Cin] bf16 contiguous; weight: [Cout,Cin,3,3,3] -> [N,D,H,W,Cout] bf16."""
+    cout, cin = weight.shape[:2]
+    if not supported(cin, cout):
+        raise ImportError(f'no tcgen05 conv instantiation for {cin}->{cout}')
+    wk, kpad = pack_fprop_weight(weight)
+    return _igemm(x.contiguous(), wk, kpad, cout)
+
+
+def conv3d_igemm_bwd(dy, x, weight, need_dx=True):
+    cout, cin = weight.shape[:2]
+    if not supported(cout, cin):
+        raise ImportError(f'no tcgen05 conv instantiation for dgrad {cout}->{cin}')
+    dx = None
+    if need_dx:
+        wd, kpad = pack_dgrad_weight(weight)
+        dx = _igemm(dy.contiguous(), wd, kpad, cin)
+    try:
+        from .conv3d_wgrad import conv3d_wgrad
+        dw = conv3d_wgrad(dy, x)
+    except ImportError:
+        # interim: cuDNN weight gradient (library) until the tcgen05 wgrad kernel lands
+        w = weight.detach().to(BF16).contiguous(memory_format=_torch.channels_last_3d)
+        _, dw, _ = _torch.ops.aten.convolution_backward(
+            dy.permute(0, 4, 1, 2, 3), x.permute(0, 4, 1, 2, 3), w, None, [1, 1, 1], [1, 1, 1], [1, 1, 1], False,
+            [0, 0, 0], 1, [False, True, False])
+        dw = dw.float()
+    return dx, dw

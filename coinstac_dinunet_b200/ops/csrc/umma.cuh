@@ -107,7 +107,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }  // namespace coinn
 
 // ---- host side: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda) ----
-#ifndef __CUDA_ARCH__
 #include <cudaTypedefs.h>
 namespace coinn {
 inline PFN_cuTensorMapEncodeTiled_v12000 get_tensor_map_encoder() {
@@ -135,4 +134,3 @@ inline int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, 
     return (int)r;
 }
 }  // namespace coinn
-#endif

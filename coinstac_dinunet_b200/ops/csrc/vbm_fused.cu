@@ -1,0 +1,501 @@
+// Fused per-site kernels of the VBM 3-D CNN blocks: channels-last (NDHWC) bf16
+// activations, everything elementwise/normalisation/pooling folded into as few passes over HBM as
+// training-mode BatchNorm allows.
+//
+//   conv1_fwd_kernel          Conv3d(1 -> 16, k3 p1) on CUDA cores (K = 27 is tensor-core hostile) + per-channel
+//                             sum / sum-of-squares in the same pass (BatchNorm batch statistics)
+//   bn_stats_kernel           sum / sumsq of a [M, C] bf16 tensor (statistics for the tcgen05 conv outputs)
+//   bn_relu_pool_fwd_kernel   y -> maxpool2(relu(bn(y)))  : reads y once, writes 1/8 of it
+//   bn_relu_pool_bwd_stats    dgamma, dbeta of the fused block from (y, dpooled)  [pass A]
+//   bn_relu_pool_bwd_apply    dy of the fused block (full resolution)              [pass B]
+//   conv1_wgrad_kernel        dW1[16,27] = sum_vox dy[vox,:] (x) x[vox + tap]
+//
+// The PyTorch chain for one block (conv -> BN -> ReLU -> MaxPool, autocast bf16) moves ~10x the bytes of this.
+#include "common.cuh"
+
+namespace coinn {
+
+struct Dims { int N, D, H, W; };
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv1: x [N,D,H,W] (fp32 or bf16, single channel) -> y [N,D,H,W,16] bf16, + stats[0:16]=sum, [16:32]=sumsq
+// Each thread produces VOX consecutive-w output voxels x 16 channels, weights broadcast from shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int C1_OUT = 16;
+constexpr int C1_VOX = 4;
+
+template <typename TIn>
+__device__ __forceinline__ float load_in(const TIn* p);
+template <> __device__ __forceinline__ float load_in<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float load_in<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) conv1_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ w /*[16][27]*/,
+                                                        __nv_bfloat16* __restrict__ y, float* __restrict__ stats, Dims d) {
+    __shared__ float4 ws[27][4];              // [tap][co/4] -> 4 consecutive output channels
+    __shared__ float red[2 * C1_OUT];
+    for (int i = threadIdx.x; i < 27 * C1_OUT; i += blockDim.x) {
+        const int tap = i / C1_OUT, co = i % C1_OUT;
+        reinterpret_cast<float*>(&ws[tap][0])[co] = w[co * 27 + tap];
+    }
+    if (threadIdx.x < 2 * C1_OUT) red[threadIdx.x] = 0.f;
+    __syncthreads();
+
+    const int wgroups = (d.W + C1_VOX - 1) / C1_VOX;
+    const long long total = (long long)d.N * d.D * d.H * wgroups;
+    float s1[C1_OUT], s2[C1_OUT];
+#pragma unroll
+    for (int c = 0; c < C1_OUT; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const int wg = (int)(g % wgroups);
+        long long t = g / wgroups;
+        const int h = (int)(t % d.H); t /= d.H;
+        const int dd = (int)(t % d.D);
+        const int n = (int)(t / d.D);
+        const int w0 = wg * C1_VOX;
+
+        float acc[C1_VOX][C1_OUT];
+#pragma unroll
+        for (int v = 0; v < C1_VOX; ++v)
+#pragma unroll
+            for (int c = 0; c < C1_OUT; ++c) acc[v][c] = 0.f;
+
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd) {
+            const int zd = dd + kd - 1;
+            if (zd < 0 || zd >= d.D) continue;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const int zh = h + kh - 1;
+                if (zh < 0 || zh >= d.H) continue;
+                const TIn* row = x + (((long long)n * d.D + zd) * d.H + zh) * d.W;
+                float in[C1_VOX + 2];
+#pragma unroll
+                for (int j = 0; j < C1_VOX + 2; ++j) {
+                    const int zw = w0 + j - 1;
+                    in[j] = (zw >= 0 && zw < d.W) ? load_in<TIn>(row + zw) : 0.f;
+                }
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int tap = (kd * 3 + kh) * 3 + kw;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 wv = ws[tap][q];
+#pragma unroll
+                        for (int v = 0; v < C1_VOX; ++v) {
+                            const float xv = in[v + kw];
+                            acc[v][4 * q + 0] = fmaf(xv, wv.x, acc[v][4 * q + 0]);
+                            acc[v][4 * q + 1] = fmaf(xv, wv.y, acc[v][4 * q + 1]);
+                            acc[v][4 * q + 2] = fmaf(xv, wv.z, acc[v][4 * q + 2]);
+                            acc[v][4 * q + 3] = fmaf(xv, wv.w, acc[v][4 * q + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        __nv_bfloat16* out = y + ((((long long)n * d.D + dd) * d.H + h) * d.W + w0) * C1_OUT;
+#pragma unroll
+        for (int v = 0; v < C1_VOX; ++v) {
+            if (w0 + v >= d.W) break;
+            float r[8], r2[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { r[c] = acc[v][c]; r2[c] = acc[v][8 + c]; }
+            const uint4 lo = pack8(r), hi = pack8(r2);
+            // statistics of the *stored* (bf16-rounded) values: exactly what BatchNorm normalises later
+            float q[8];
+            unpack8(lo, q);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { s1[c] += q[c]; s2[c] = fmaf(q[c], q[c], s2[c]); }
+            unpack8(hi, q);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { s1[8 + c] += q[c]; s2[8 + c] = fmaf(q[c], q[c], s2[8 + c]); }
+            reinterpret_cast<uint4*>(out + v * C1_OUT)[0] = lo;
+            reinterpret_cast<uint4*>(out + v * C1_OUT)[1] = hi;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C1_OUT; ++c) {
+        const float a = warp_sum(s1[c]), b = warp_sum(s2[c]);
+        if (lane_id() == 0) { atomicAdd(&red[c], a); atomicAdd(&red[C1_OUT + c], b); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * C1_OUT) atomicAdd(&stats[threadIdx.x], red[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stats[0:C] = sum_m y[m,c], stats[C:2C] = sum_m y[m,c]^2      (y: [M, C] bf16, C % 8 == 0, C <= 256)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ stats,
+                                                       long long M, int C) {
+    extern __shared__ float sm[];                       // [2*C]
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int chunks = C >> 3;                          // 16-byte chunks per row
+    // thread owns one fixed channel chunk (so partial sums stay in registers) and strides over rows
+    const int my_chunk = threadIdx.x % chunks;
+    const int rows_per_iter = blockDim.x / chunks;
+    const int my_row_off = threadIdx.x / chunks;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    if (my_row_off < rows_per_iter) {
+        for (long long m = (long long)blockIdx.x * rows_per_iter + my_row_off; m < M; m += (long long)gridDim.x * rows_per_iter) {
+            const uint4 u = ld_stream_u4(reinterpret_cast<const uint4*>(y + m * C) + my_chunk);
+            float f[8];
+            unpack8(u, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sm[my_chunk * 8 + j], s1[j]);
+            atomicAdd(&sm[C + my_chunk * 8 + j], s2[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[i], sm[i]);
+}
+
+// mean / invstd from sums; optionally update running stats (PyTorch semantics: unbiased running var)
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float count, float eps, float momentum, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float mu = stats[c] / count;
+    const float var = fmaxf(stats[C + c] / count - mu * mu, 0.f);
+    mean[c] = mu;
+    invstd[c] = rsqrtf(var + eps);
+    if (running_mean) {
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+        const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// p[n, d/2, h/2, w/2, c] = max over the 2x2x2 window of relu(scale[c] * y + shift[c])
+// one thread = one pooled voxel x 8 channels (a 16-byte chunk)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, __nv_bfloat16* __restrict__ p,
+                                                               Dims d, int C) {
+    const int chunks = C >> 3;
+    const int PD = d.D >> 1, PH = d.H >> 1, PW = d.W >> 1;
+    const long long total = (long long)d.N * PD * PH * PW * chunks;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        long long t = i / chunks;
+        const int pw = (int)(t % PW); t /= PW;
+        const int ph = (int)(t % PH); t /= PH;
+        const int pd = (int)(t % PD);
+        const int n = (int)(t / PD);
+        float sc[8], sh[8], best[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = ch * 8 + j;
+            sc[j] = gamma[c] * invstd[c];
+            sh[j] = beta[c] - mean[c] * sc[j];
+            best[j] = 0.f;                               // relu floor
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int zd = 2 * pd + (k >> 2), zh = 2 * ph + ((k >> 1) & 1), zw = 2 * pw + (k & 1);
+            const long long vox = (((long long)n * d.D + zd) * d.H + zh) * d.W + zw;
+            const uint4 u = ld_stream_u4(reinterpret_cast<const uint4*>(y + vox * C) + ch);
+            float f[8];
+            unpack8(u, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], fmaf(f[j], sc[j], sh[j]));
+        }
+        reinterpret_cast<uint4*>(p + (i / chunks) * C)[ch] = pack8(best);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of the fused block.  For every pooled voxel: recompute z = relu(bn(y)) on its window, route dp to the
+// first arg-max (PyTorch tie rule), zero if the max is not positive.
+//   pass A: dbeta[c] = sum dz ; dgamma[c] = sum dz * xhat            (acc[0:C] = dbeta, acc[C:2C] = dgamma)
+//   pass B: dy = gamma*invstd * (dz - dbeta/M - xhat * dgamma/M)     for ALL voxels (incl. odd borders)
+// ------------------------------------------------------------------------------------------------
+template <bool APPLY>
+__global__ void __launch_bounds__(256) bn_relu_pool_bwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dp,
+                                                               const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float* __restrict__ acc, __nv_bfloat16* __restrict__ dy,
+                                                               Dims d, int C, float inv_count) {
+    extern __shared__ float sm[];                        // pass A: [2*C] block partials
+    const int chunks = C >> 3;
+    if (!APPLY) {
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+        __syncthreads();
+    }
+    // windows cover ceil(dim/2) cells so that odd border voxels (not pooled) still get their dy in pass B
+    const int PD = d.D >> 1, PH = d.H >> 1, PW = d.W >> 1;
+    const int CD = (d.D + 1) >> 1, CH = (d.H + 1) >> 1, CW = (d.W + 1) >> 1;
+    const int my_chunk = threadIdx.x % chunks;
+    const int cells_per_iter = blockDim.x / chunks;
+    const int my_cell_off = threadIdx.x / chunks;
+    const long long total_cells = (long long)d.N * CD * CH * CW;
+
+    float sc[8], sh[8], gi[8], mu[8], is[8], db[8], dg[8], a_db[8], a_dg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = my_chunk * 8 + j;
+        mu[j] = mean[c]; is[j] = invstd[c];
+        sc[j] = gamma[c] * is[j];
+        sh[j] = beta[c] - mu[j] * sc[j];
+        gi[j] = sc[j];
+        a_db[j] = 0.f; a_dg[j] = 0.f;
+        if (APPLY) { db[j] = acc[c] * inv_count; dg[j] = acc[C + c] * inv_count; }
+    }
+    if (my_cell_off < cells_per_iter) {
+        for (long long cell = (long long)blockIdx.x * cells_per_iter + my_cell_off; cell < total_cells;
+             cell += (long long)gridDim.x * cells_per_iter) {
+            long long t = cell;
+            const int pw = (int)(t % CW); t /= CW;
+            const int ph = (int)(t % CH); t /= CH;
+            const int pd = (int)(t % CD);
+            const int n = (int)(t / CD);
+            const bool pooled = pd < PD && ph < PH && pw < PW;
+            float g[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = 0.f;
+            if (pooled) {
+                const long long pv = (((long long)n * PD + pd) * PH + ph) * PW + pw;
+                unpack8(ld_stream_u4(reinterpret_cast<const uint4*>(dp + pv * C) + my_chunk), g);
+            } else if (!APPLY) {
+                continue;                                // no gradient flows through un-pooled borders
+            }
+            float yv[8][8];
+            float best[8]; int arg[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int zd = 2 * pd + (k >> 2), zh = 2 * ph + ((k >> 1) & 1), zw = 2 * pw + (k & 1);
+                if (zd < d.D && zh < d.H && zw < d.W) {
+                    const long long vox = (((long long)n * d.D + zd) * d.H + zh) * d.W + zw;
+                    unpack8(ld_stream_u4(reinterpret_cast<const uint4*>(y + vox * C) + my_chunk), yv[k]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) yv[k][j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float z = fmaf(yv[k][j], sc[j], sh[j]);
+                    if (z > best[j]) { best[j] = z; arg[j] = k; }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (!(best[j] > 0.f) || !pooled) g[j] = 0.f;   // relu'(<=0) = 0
+            if (!APPLY) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (yv[0][j] - mu[j]) * is[j];     // placeholder, replaced below per arg
+                    (void)xh;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (arg[j] == k) { a_db[j] += g[j]; a_dg[j] = fmaf(g[j], (yv[k][j] - mu[j]) * is[j], a_dg[j]); }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int zd = 2 * pd + (k >> 2), zh = 2 * ph + ((k >> 1) & 1), zw = 2 * pw + (k & 1);
+                    if (!(zd < d.D && zh < d.H && zw < d.W)) continue;
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float dz = (arg[j] == k) ? g[j] : 0.f;
+                        const float xh = (yv[k][j] - mu[j]) * is[j];
+                        o[j] = gi[j] * (dz - db[j] - xh * dg[j]);
+                    }
+                    const long long vox = (((long long)n * d.D + zd) * d.H + zh) * d.W + zw;
+                    reinterpret_cast<uint4*>(dy + vox * C)[my_chunk] = pack8(o);
+                }
+            }
+        }
+    }
+    if (!APPLY) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sm[my_chunk * 8 + j], a_db[j]);
+            atomicAdd(&sm[C + my_chunk * 8 + j], a_dg[j]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&acc[i], sm[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv1 wgrad: dW[co, tap] += sum_vox dy[vox, co] * x[vox + tap]      (dy: [N,D,H,W,16] bf16, x: [N,D,H,W])
+// lane = tap (27 of 32 lanes active), 16 output channels in registers, dy row broadcast from shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_TILE_W = 64;            // voxels (along w) staged per step
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x,
+                                                          float* __restrict__ dw /*[16][27]*/, Dims d) {
+    __shared__ __align__(16) __nv_bfloat16 s_dy[8][WG_TILE_W][C1_OUT];     // per warp
+    __shared__ float s_x[8][3][3][WG_TILE_W + 2];                          // per warp: halo rows
+    __shared__ float s_acc[C1_OUT * 27];
+    for (int i = threadIdx.x; i < C1_OUT * 27; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int nwarps = blockDim.x >> 5;
+    const int wtiles = (d.W + WG_TILE_W - 1) / WG_TILE_W;
+    const long long total = (long long)d.N * d.D * d.H * wtiles;
+    const int tap = lane < 27 ? lane : 26;
+    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+    float acc[C1_OUT];
+#pragma unroll
+    for (int c = 0; c < C1_OUT; ++c) acc[c] = 0.f;
+
+    for (long long job = (long long)blockIdx.x * nwarps + warp; job < total; job += (long long)gridDim.x * nwarps) {
+        const int wt = (int)(job % wtiles);
+        long long t = job / wtiles;
+        const int h = (int)(t % d.H); t /= d.H;
+        const int dd = (int)(t % d.D);
+        const int n = (int)(t / d.D);
+        const int w0 = wt * WG_TILE_W;
+        const int nw = min(WG_TILE_W, d.W - w0);
+        __syncwarp();
+        // stage dy rows (nw voxels x 32 bytes) and the 3x3 halo rows of x
+        const uint4* src = reinterpret_cast<const uint4*>(dy + ((((long long)n * d.D + dd) * d.H + h) * d.W + w0) * C1_OUT);
+        for (int i = lane; i < nw * 2; i += 32) reinterpret_cast<uint4*>(&s_dy[warp][0][0])[i] = ld_stream_u4(src + i);
+        for (int r = 0; r < 9; ++r) {
+            const int zd = dd + r / 3 - 1, zh = h + r % 3 - 1;
+            const bool ok = zd >= 0 && zd < d.D && zh >= 0 && zh < d.H;
+            const TIn* row = x + (((long long)n * d.D + zd) * d.H + zh) * d.W;
+            for (int j = lane; j < nw + 2; j += 32) {
+                const int zw = w0 + j - 1;
+                s_x[warp][r / 3][r % 3][j] = (ok && zw >= 0 && zw < d.W) ? load_in<TIn>(row + zw) : 0.f;
+            }
+        }
+        __syncwarp();
+        for (int v = 0; v < nw; ++v) {
+            const float xv = s_x[warp][kd][kh][v + kw];
+            const uint4 lo = reinterpret_cast<const uint4*>(&s_dy[warp][v][0])[0];
+            const uint4 hi = reinterpret_cast<const uint4*>(&s_dy[warp][v][0])[1];
+            float g[8];
+            unpack8(lo, g);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = fmaf(g[c], xv, acc[c]);
+            unpack8(hi, g);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[8 + c] = fmaf(g[c], xv, acc[8 + c]);
+        }
+    }
+    if (lane < 27) {
+#pragma unroll
+        for (int c = 0; c < C1_OUT; ++c) atomicAdd(&s_acc[c * 27 + lane], acc[c]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C1_OUT * 27; i += blockDim.x) atomicAdd(&dw[i], s_acc[i]);
+}
+
+static inline int grid_for(long long work_items, int threads, int per_thread = 4) {
+    long long want = (work_items + (long long)threads * per_thread - 1) / ((long long)threads * per_thread);
+    const long long cap = 8LL * B200_SM_COUNT;
+    return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+}  // namespace coinn
+
+using coinn::Dims;
+
+// x_dtype: 0 fp32, 1 bf16.  stats must be zeroed (2*16 floats).
+COINN_API int coinn_conv1_fwd(const void* x, int x_dtype, const float* w, void* y, float* stats,
+                              int N, int D, int H, int W, void* stream) {
+    using namespace coinn;
+    Dims d{N, D, H, W};
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long groups = (long long)N * D * H * ((W + C1_VOX - 1) / C1_VOX);
+    const int grid = grid_for(groups, 256, 2);
+    if (x_dtype == 0) conv1_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, w, (__nv_bfloat16*)y, stats, d);
+    else conv1_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, stats, d);
+    COINN_CHECK_LAUNCH();
+    return 0;
+}
+
+COINN_API int coinn_bn_stats(const void* y, float* stats, long long M, int C, void* stream) {
+    using namespace coinn;
+    if (C % 8 || C > 256 || 256 % (C / 8)) return (int)cudaErrorInvalidValue;
+    const int rows_per_iter = 256 / (C / 8);
+    long long want = (M + (long long)rows_per_iter * 16 - 1) / ((long long)rows_per_iter * 16);
+    const int grid = (int)(want < 1 ? 1 : (want > 4LL * B200_SM_COUNT ? 4LL * B200_SM_COUNT : want));
+    bn_stats_kernel<<<grid, 256, 2 * C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const __nv_bfloat16*)y, stats, M, C);
+    COINN_CHECK_LAUNCH();
+    return 0;
+}
+
+COINN_API int coinn_bn_finalize(const float* stats, float* mean, float* invstd, float* running_mean, float* running_var,
+                                float count, float eps, float momentum, int C, void* stream) {
+    coinn::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        stats, mean, invstd, running_mean, running_var, count, eps, momentum, C);
+    COINN_CHECK_LAUNCH();
+    return 0;
+}
+
+COINN_API int coinn_bn_relu_pool_fwd(const void* y, const float* mean, const float* invstd, const float* gamma,
+                                     const float* beta, void* p, int N, int D, int H, int W, int C, void* stream) {
+    using namespace coinn;
+    if (C % 8) return (int)cudaErrorInvalidValue;
+    Dims d{N, D, H, W};
+    const long long total = (long long)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
+    if (total == 0) return 0;
+    bn_relu_pool_fwd_kernel<<<grid_for(total, 256, 2), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const __nv_bfloat16*)y, mean, invstd, gamma, beta, (__nv_bfloat16*)p, d, C);
+    COINN_CHECK_LAUNCH();
+    return 0;
+}
+
+// apply == 0: acc[2C] (zeroed) += (dbeta, dgamma).  apply == 1: writes dy using acc.
+COINN_API int coinn_bn_relu_pool_bwd(const void* y, const void* dp, const float* mean, const float* invstd,
+                                     const float* gamma, const float* beta, float* acc, void* dy,
+                                     int N, int D, int H, int W, int C, int apply, void* stream) {
+    using namespace coinn;
+    if (C % 8 || C > 256 || 256 % (C / 8)) return (int)cudaErrorInvalidValue;
+    Dims d{N, D, H, W};
+    const int cells_per_iter = 256 / (C / 8);
+    const long long cells = (long long)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
+    long long want = (cells + (long long)cells_per_iter * 2 - 1) / ((long long)cells_per_iter * 2);
+    const int grid = (int)(want < 1 ? 1 : (want > 8LL * B200_SM_COUNT ? 8LL * B200_SM_COUNT : want));
+    const float inv_count = 1.f / ((float)N * D * H * W);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (apply) bn_relu_pool_bwd_kernel<true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)dp, mean, invstd,
+                                                                   gamma, beta, acc, (__nv_bfloat16*)dy, d, C, inv_count);
+    else bn_relu_pool_bwd_kernel<false><<<grid, 256, 2 * C * sizeof(float), st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)dp, mean,
+                                                                                   invstd, gamma, beta, acc, nullptr, d, C, inv_count);
+    COINN_CHECK_LAUNCH();
+    return 0;
+}
+
+// dw[16*27] must be zeroed.
+COINN_API int coinn_conv1_wgrad(const void* dy, const void* x, int x_dtype, float* dw, int N, int D, int H, int W, void* stream) {
+    using namespace coinn;
+    Dims d{N, D, H, W};
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long jobs = (long long)N * D * H * ((W + WG_TILE_W - 1) / WG_TILE_W);
+    long long want = (jobs + 8 * 4 - 1) / (8 * 4);
+    const int grid = (int)(want < 1 ? 1 : (want > 4LL * B200_SM_COUNT ? 4LL * B200_SM_COUNT : want));
+    if (x_dtype == 0) conv1_wgrad_kernel<float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const float*)x, dw, d);
+    else conv1_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, d);
+    COINN_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,119 @@
+"""Linear layers on the hand-written tcgen05 GEMM (``csrc/gemm_tcgen05.cu``).
+
+``gemm_tn(A, B)`` computes ``A[M,K] @ B[N,K].T`` in bf16 with fp32 accumulation in TMEM.  The three
+GEMMs of a Linear layer map onto it as
+    forward  y  = gemm_tn(x,  W)                      [M,N]   (+bias, +ReLU fused in the epilogue)
+    dgrad    dx = gemm_tn(dy, W^T contiguous)         [M,K]
+    wgrad    dW = gemm_tn(dy^T, x^T) in fp32          [N,K]
+Small-M problems (batch 8-16) are split along K so that ~148 CTAs stream the weight matrix.
+"""
+import torch as _torch
+
+from . import native as _nat
+
+_SMS = 148
+
+
+def _bump():
+    from . import _count_launch
+    _count_launch()
+
+
+def gemm_tn(a, b, bias=None, relu=False, out_dtype=_torch.bfloat16, bias_mode=1, split_k=None, out=None):
+    """``a[M,K] @ b[N,K].T`` -> ``[M,N]``.  a, b: bf16, row-major, K % 8 == 0."""
+    assert a.is_cuda and b.is_cuda and a.dtype == _torch.bfloat16 and b.dtype == _torch.bfloat16
+    M, K = a.shape
+    N, K2 = b.shape
+    assert K == K2, (a.shape, b.shape)
+    if K % 8:  # TMA needs 16-byte aligned row strides: pad K with zeros (exact)
+        pad = 8 - K % 8
+        a = _torch.nn.functional.pad(a, (0, pad))
+        b = _torch.nn.functional.pad(b, (0, pad))
+        K += pad
+    a, b = a.contiguous(), b.contiguous()
+    if split_k is None:
+        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        kblocks = (K + 63) // 64
+        split_k = max(1, min(kblocks // 4, _SMS // tiles)) if tiles * 2 <= _SMS else 1
+    fused_epilogue = split_k <= 1
+    if fused_epilogue:
+        c = out if out is not None else _torch.empty((M, N), dtype=out_dtype, device=a.device)
+        code = 0 if c.dtype == _torch.bfloat16 else 1
+        assert c.dtype in (_torch.bfloat16, _torch.float32) and c.is_contiguous()
+        bias_t = bias.float().contiguous() if bias is not None else None
+        _nat.check(_nat.lib().coinn_gemm_bf16_tn(a.data_ptr(), b.data_ptr(), c.data_ptr(),
+                                                 bias_t.data_ptr() if bias_t is not None else None,
+                                                 M, N, K, K, K, N, code, int(relu), int(bias_mode), 1,
+                                                 _nat.stream_ptr(a.device)), 'coinn_gemm_bf16_tn')
+        _bump()
+        return c
+    acc = _torch.zeros((M, N), dtype=_torch.float32, device=a.device)
+    _nat.check(_nat.lib().coinn_gemm_bf16_tn(a.data_ptr(), b.data_ptr(), acc.data_ptr(), None, M, N, K, K, K, N,
+                                             1, 0, 0, int(split_k), _nat.stream_ptr(a.device)), 'coinn_gemm_bf16_tn')
+    _bump()
+    if bias is not None:
+        acc = acc + (bias.float() if bias_mode == 1 else bias.float().unsqueeze(1))
+    if relu:
+        acc = acc.relu_()
+    res = acc if out_dtype == _torch.float32 else acc.to(out_dtype)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+class LinearFn(_torch.autograd.Function):
+    """y = relu?(x @ W^T + b) with all three GEMMs on tcgen05.  x: [M,K] any float dtype."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        xb = x.to(_torch.bfloat16).contiguous()
+        wb = weight.to(_torch.bfloat16).contiguous()
+        y = gemm_tn(xb, wb, bias=bias, relu=relu, out_dtype=_torch.bfloat16)
+        ctx.save_for_backward(xb, wb, y if relu else None)
+        ctx.relu, ctx.has_bias = relu, bias is not None
+        ctx.in_dtype, ctx.w_dtype = x.dtype, weight.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, wb, y = ctx.saved_tensors
+        dy = dy.to(_torch.bfloat16)
+        if ctx.relu:
+            dy = dy * (y > 0)
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_tn(dy, wb.t().contiguous(), out_dtype=_torch.bfloat16).to(ctx.in_dtype)
+        if ctx.needs_input_grad[1]:
+            dw = gemm_tn(dy.t().contiguous(), xb.t().contiguous(), out_dtype=_torch.float32).to(ctx.w_dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.float().sum(0)
+        return dx, dw, db, None
+
+
+class B200Linear(_torch.nn.Linear):
+    """Drop-in ``nn.Linear`` whose forward/backward run on the tcgen05 GEMM (optionally with the
+    following ReLU fused into the epilogue)."""
+    is_native = True
+
+    def __init__(self, in_features, out_features, bias=True, fuse_relu=False, **kw):
+        super().__init__(in_features, out_features, bias=bias, **kw)
+        self.fuse_relu = fuse_relu
+
+    @classmethod
+    def from_linear(cls, lin, fuse_relu=False):
+        new = cls.__new__(cls)
+        _torch.nn.Module.__init__(new)
+        new.in_features, new.out_features = lin.in_features, lin.out_features
+        new.weight, new.bias = lin.weight, lin.bias
+        new.fuse_relu = fuse_relu
+        return new
+
+    def forward(self, x):
+        if not x.is_cuda:
+            y = _torch.nn.functional.linear(x, self.weight, self.bias)
+            return y.relu() if self.fuse_relu else y
+        lead = x.shape[:-1]
+        y = LinearFn.apply(x.reshape(-1, x.shape[-1]), self.weight, self.bias, self.fuse_relu)
+        return y.reshape(*lead, self.out_features)

@@ -39,8 +39,14 @@ class _Lib:
         d.coinn_count.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong,
                                   C.c_int, C.c_int, C.c_void_p]
         d.coinn_orthogonalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
-        for name in dir(self):
-            pass
+        d.coinn_gemm_bf16_tn.argtypes = [C.c_void_p] * 4 + [C.c_int] * 10 + [C.c_void_p]
+        d.coinn_conv1_fwd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
+        d.coinn_bn_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
+        d.coinn_bn_finalize.argtypes = [C.c_void_p] * 5 + [C.c_float] * 3 + [C.c_int, C.c_void_p]
+        d.coinn_bn_relu_pool_fwd.argtypes = [C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p]
+        d.coinn_bn_relu_pool_bwd.argtypes = [C.c_void_p] * 8 + [C.c_int] * 6 + [C.c_void_p]
+        d.coinn_conv3d_igemm.argtypes = [C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p]
+        d.coinn_conv1_wgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
 
     def __getattr__(self, name):
         return getattr(self.dll, name)

@@ -1,0 +1,173 @@
+"""Fused blocks of the VBM 3-D CNN on the hand-written kernels (``csrc/vbm_fused.cu`` +
+``csrc/conv3d_tcgen05.cu``).  Activations are channels-last ``[N, D, H, W, C]`` bf16.
+
+One ``ConvBnReluPool`` block = Conv3d(k3, p1, no bias) -> BatchNorm3d (batch statistics) -> ReLU ->
+MaxPool3d(2).  Passes over HBM per block:
+
+    forward   conv (writes y)  ->  stats (reads y; fused into conv1)  ->  bn+relu+pool (reads y, writes y/8)
+    backward  pass A (reads y, dp -> dgamma, dbeta)  ->  pass B (reads y, dp, writes dy)  ->  dgrad + wgrad
+
+versus conv, BN-stat, BN-apply, ReLU, pool (each a full read+write) in the PyTorch chain - whose
+channels-last-3d BatchNorm backward alone takes 40 ms per step on a B200 (profiles/r1_launches_torch.txt).
+"""
+import torch as _torch
+
+from . import native as _nat
+
+BF16 = _torch.bfloat16
+
+
+def _bump(n=1):
+    from . import _count_launch
+    _count_launch(n)
+
+
+def _sp(t):
+    return _nat.stream_ptr(t.device)
+
+
+def _chk(code, what):
+    _nat.check(code, what)
+
+
+# ------------------------------------------------------------------------------------ kernels
+def conv1_fwd(x, weight):
+    """x: [N,D,H,W] fp32/bf16 (single channel), weight: [16,1,3,3,3] -> (y [N,D,H,W,16] bf16, stats[32])."""
+    N, D, H, W = x.shape
+    x = x.contiguous()
+    w = weight.detach().float().reshape(16, 27).contiguous()
+    y = _torch.empty((N, D, H, W, 16), dtype=BF16, device=x.device)
+    stats = _torch.zeros(32, dtype=_torch.float32, device=x.device)
+    _chk(_nat.lib().coinn_conv1_fwd(x.data_ptr(), 0 if x.dtype == _torch.float32 else 1, w.data_ptr(), y.data_ptr(),
+                                    stats.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_fwd')
+    _bump()
+    return y, stats
+
+
+def conv1_wgrad(dy, x):
+    """dy: [N,D,H,W,16] bf16, x: [N,D,H,W] -> dW [16,1,3,3,3] fp32."""
+    N, D, H, W = x.shape
+    dw = _torch.zeros(16 * 27, dtype=_torch.float32, device=x.device)
+    _chk(_nat.lib().coinn_conv1_wgrad(dy.data_ptr(), x.data_ptr(), 0 if x.dtype == _torch.float32 else 1,
+                                      dw.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_wgrad')
+    _bump()
+    return dw.view(16, 1, 3, 3, 3)
+
+
+def bn_stats(y):
+    """[..., C] bf16 -> stats[2C] = (sum, sumsq) over all leading dims."""
+    C = y.shape[-1]
+    stats = _torch.zeros(2 * C, dtype=_torch.float32, device=y.device)
+    _chk(_nat.lib().coinn_bn_stats(y.data_ptr(), stats.data_ptr(), y.numel() // C, C, _sp(y)), 'coinn_bn_stats')
+    _bump()
+    return stats
+
+
+def bn_finalize(stats, count, eps, momentum, running_mean=None, running_var=None):
+    C = stats.numel() // 2
+    mean = _torch.empty(C, dtype=_torch.float32, device=stats.device)
+    invstd = _torch.empty_like(mean)
+    _chk(_nat.lib().coinn_bn_finalize(stats.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                      running_mean.data_ptr() if running_mean is not None else None,
+                                      running_var.data_ptr() if running_var is not None else None,
+                                      float(count), float(eps), float(momentum), C, _sp(stats)), 'coinn_bn_finalize')
+    _bump()
+    return mean, invstd
+
+
+def bn_relu_pool_fwd(y, mean, invstd, gamma, beta):
+    N, D, H, W, C = y.shape
+    p = _torch.empty((N, D // 2, H // 2, W // 2, C), dtype=BF16, device=y.device)
+    _chk(_nat.lib().coinn_bn_relu_pool_fwd(y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                           beta.data_ptr(), p.data_ptr(), N, D, H, W, C, _sp(y)), 'bn_relu_pool_fwd')
+    _bump()
+    return p
+
+
+def bn_relu_pool_bwd(y, dp, mean, invstd, gamma, beta):
+    """-> (dy [N,D,H,W,C] bf16, dgamma [C], dbeta [C])"""
+    N, D, H, W, C = y.shape
+    acc = _torch.zeros(2 * C, dtype=_torch.float32, device=y.device)
+    dy = _torch.empty_like(y)
+    args = (y.data_ptr(), dp.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+            acc.data_ptr())
+    _chk(_nat.lib().coinn_bn_relu_pool_bwd(*args, None, N, D, H, W, C, 0, _sp(y)), 'bn_relu_pool_bwd[A]')
+    _chk(_nat.lib().coinn_bn_relu_pool_bwd(*args, dy.data_ptr(), N, D, H, W, C, 1, _sp(y)), 'bn_relu_pool_bwd[B]')
+    _bump(2)
+    return dy, acc[C:], acc[:C]
+
+
+# ------------------------------------------------------------------------------------- convs
+def _as_ncdhw(x_ndhwc):
+    return x_ndhwc.permute(0, 4, 1, 2, 3)          # logical NCDHW, channels_last_3d strides (no copy)
+
+
+def conv3d_fwd(x, weight, backend='auto'):
+    """x: [N,D,H,W,Cin] bf16, weight: [Cout,Cin,3,3,3] (any float dtype) -> y [N,D,H,W,Cout] bf16."""
+    if backend in ('auto', 'tcgen05'):
+        try:
+            from .conv3d import conv3d_igemm_fwd
+            return conv3d_igemm_fwd(x, weight)
+        except ImportError:
+            if backend == 'tcgen05':
+                raise
+    w = weight.detach().to(BF16).contiguous(memory_format=_torch.channels_last_3d)
+    y = _torch.nn.functional.conv3d(_as_ncdhw(x), w, padding=1)
+    return y.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def conv3d_bwd(dy, x, weight, need_dx=True, backend='auto'):
+    """-> (dx [N,D,H,W,Cin] bf16 or None, dW [Cout,Cin,3,3,3] fp32)"""
+    if backend in ('auto', 'tcgen05'):
+        try:
+            from .conv3d import conv3d_igemm_bwd
+            return conv3d_igemm_bwd(dy, x, weight, need_dx)
+        except ImportError:
+            if backend == 'tcgen05':
+                raise
+    w = weight.detach().to(BF16).contiguous(memory_format=_torch.channels_last_3d)
+    dx, dw, _ = _torch.ops.aten.convolution_backward(
+        _as_ncdhw(dy), _as_ncdhw(x), w, None, [1, 1, 1], [1, 1, 1], [1, 1, 1], False, [0, 0, 0], 1,
+        [bool(need_dx), True, False])
+    if dx is not None:
+        dx = dx.permute(0, 2, 3, 4, 1).contiguous()
+    return dx, dw.float()
+
+
+# --------------------------------------------------------------------------------- autograd
+class ConvBnReluPoolFn(_torch.autograd.Function):
+    """One fused VBM block.  ``x``: [N,D,H,W,Cin] bf16 (or [N,D,H,W] fp32/bf16 for the first block)."""
+
+    @staticmethod
+    def forward(ctx, x, conv_w, gamma, beta, running_mean, running_var, eps, momentum, training, backend):
+        first = x.dim() == 4
+        if first:
+            y, stats = conv1_fwd(x, conv_w)
+        else:
+            y = conv3d_fwd(x, conv_w, backend)
+            stats = None
+        N, D, H, W, C = y.shape
+        g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        if training:
+            if stats is None:
+                stats = bn_stats(y)
+            mean, invstd = bn_finalize(stats, N * D * H * W, eps, momentum, running_mean, running_var)
+        else:
+            mean = running_mean.float()
+            invstd = (running_var.float() + eps).rsqrt()
+        p = bn_relu_pool_fwd(y, mean, invstd, g, b)
+        ctx.save_for_backward(x, conv_w, y, mean, invstd, g, b)
+        ctx.first, ctx.backend, ctx.training = first, backend, training
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        x, conv_w, y, mean, invstd, g, b = ctx.saved_tensors
+        dy, dgamma, dbeta = bn_relu_pool_bwd(y, dp.contiguous(), mean, invstd, g, b)
+        if not ctx.training:   # eval-mode BN has no batch-statistics terms; not a training path
+            raise RuntimeError('ConvBnReluPoolFn.backward is only defined for training-mode BatchNorm')
+        if ctx.first:
+            dx, dw = None, conv1_wgrad(dy, x)
+        else:
+            dx, dw = conv3d_bwd(dy, x, conv_w, need_dx=ctx.needs_input_grad[0], backend=ctx.backend)
+        return dx, dw.to(conv_w.dtype), dgamma.to(g.dtype), dbeta.to(b.dtype), None, None, None, None, None, None

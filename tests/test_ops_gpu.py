@@ -129,3 +129,141 @@ def test_arena_checkpoint_state_roundtrip(dev, tmp_path):
     assert int(arena2.step_count.item()) == 3
     assert torch.allclose(arena2.m, arena.m) and torch.allclose(arena2.v, arena.v)
     assert torch.equal(arena2.flat_param, arena.flat_param)
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (8, 256, 9216), (16, 2, 64), (300, 200, 136), (1, 16, 8),
+                                   (257, 129, 72), (16, 256, 66), (1024, 512, 1024)])
+def test_tcgen05_gemm_matches_fp32(dev, M, N, K):
+    from coinstac_dinunet_b200.ops.linear import gemm_tn
+    torch.manual_seed(M * 7 + N)
+    a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    b = torch.randn(N, K, device=dev).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    want = a.float() @ b.float().t()
+    for split in (1, None, 3):
+        got = gemm_tn(a, b, out_dtype=torch.float32, split_k=split)
+        assert torch.allclose(got, want, atol=1e-2 * K ** 0.5, rtol=1e-2), (split, (got - want).abs().max())
+    got = gemm_tn(a, b, bias=bias, relu=True, out_dtype=torch.bfloat16, split_k=1)
+    ref = (want + bias).relu()
+    assert torch.allclose(got.float(), ref, atol=0.05 * K ** 0.5, rtol=2e-2)
+
+
+def _rel(got, want):
+    return float((got.float() - want.float()).norm() / want.float().norm().clamp_min(1e-12))
+
+
+def test_b200_linear_autograd(dev):
+    from coinstac_dinunet_b200.ops.linear import B200Linear
+    torch.manual_seed(0)
+    ref = torch.nn.Linear(200, 72).to(dev)
+    ours = B200Linear.from_linear(torch.nn.Linear(200, 72).to(dev), fuse_relu=True)
+    ours.load_state_dict(ref.state_dict())
+    x = torch.randn(24, 200, device=dev)
+    x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y1 = ref(x1).relu(); y2 = ours(x2)
+    assert torch.allclose(y1, y2.float(), atol=0.05, rtol=0.05)
+    g = torch.randn_like(y1)
+    y1.backward(g); y2.backward(g.to(y2.dtype))
+    assert _rel(x2.grad, x1.grad) < 2e-2
+    assert _rel(ours.weight.grad, ref.weight.grad) < 2e-2
+    assert _rel(ours.bias.grad, ref.bias.grad) < 2e-2
+
+
+def _ndhwc(t):
+    return t.permute(0, 2, 3, 4, 1).contiguous()
+
+
+@pytest.mark.parametrize('shape', [(2, 9, 11, 13), (1, 8, 8, 8), (3, 5, 6, 70)])
+def test_conv1_fwd_and_wgrad(dev, shape):
+    from coinstac_dinunet_b200.ops import vbm
+    torch.manual_seed(1)
+    N, D, H, W = shape
+    x = torch.randn(N, D, H, W, device=dev)
+    w = torch.randn(16, 1, 3, 3, 3, device=dev) * 0.2
+    y, stats = vbm.conv1_fwd(x, w)
+    ref = torch.nn.functional.conv3d(x.unsqueeze(1), w, padding=1)
+    assert _rel(y, _ndhwc(ref)) < 5e-3
+    yb = y.float().reshape(-1, 16)
+    assert torch.allclose(stats[:16], yb.sum(0), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(stats[16:], (yb * yb).sum(0), rtol=1e-3, atol=1e-2)
+    dy = torch.randn(N, D, H, W, 16, device=dev).to(torch.bfloat16)
+    dw = vbm.conv1_wgrad(dy, x)
+    _, dw_ref, _ = torch.ops.aten.convolution_backward(
+        dy.float().permute(0, 4, 1, 2, 3), x.unsqueeze(1), w, None, [1, 1, 1], [1, 1, 1], [1, 1, 1], False,
+        [0, 0, 0], 1, [False, True, False])
+    assert _rel(dw, dw_ref) < 2e-3
+
+
+@pytest.mark.parametrize('C,shape', [(16, (2, 9, 10, 13)), (32, (1, 6, 6, 6)), (128, (2, 4, 7, 5)), (256, (2, 3, 4, 3))])
+def test_bn_relu_pool_block_matches_torch(dev, C, shape):
+    """fused stats + BN + ReLU + MaxPool forward and backward vs the PyTorch op chain (fp32)."""
+    from coinstac_dinunet_b200.ops import vbm
+    torch.manual_seed(C)
+    N, D, H, W = shape
+    y = (torch.randn(N, D, H, W, C, device=dev) * 2 + 0.3).to(torch.bfloat16)
+    gamma = torch.rand(C, device=dev) + 0.5
+    gamma[::3] *= -1                                        # negative scales must work too
+    beta = torch.randn(C, device=dev) * 0.1
+    stats = vbm.bn_stats(y)
+    yf = y.float().reshape(-1, C)
+    assert torch.allclose(stats[:C], yf.sum(0), rtol=1e-3, atol=1e-2)
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    mean, invstd = vbm.bn_finalize(stats, yf.shape[0], 1e-5, 0.1, rm, rv)
+    p = vbm.bn_relu_pool_fwd(y, mean, invstd, gamma, beta)
+
+    y_ref = y.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    bn = torch.nn.BatchNorm3d(C).to(dev)
+    with torch.no_grad():
+        bn.weight.copy_(gamma); bn.bias.copy_(beta)
+    p_ref = torch.nn.functional.max_pool3d(torch.relu(bn(y_ref)), 2)
+    assert _rel(p, _ndhwc(p_ref)) < 1e-2
+    assert torch.allclose(rm, bn.running_mean, atol=1e-3) and torch.allclose(rv, bn.running_var, rtol=1e-3, atol=1e-3)
+
+    dp = torch.randn_like(p_ref)
+    p_ref.backward(dp)
+    dy, dgamma, dbeta = vbm.bn_relu_pool_bwd(y, _ndhwc(dp).to(torch.bfloat16), mean, invstd, gamma, beta)
+    assert _rel(dgamma, bn.weight.grad) < 2e-2 and _rel(dbeta, bn.bias.grad) < 2e-2
+    assert _rel(dy, _ndhwc(y_ref.grad)) < 2e-2
+
+
+def test_native_vbmnet_matches_torch_reference(dev):
+    """whole model: native kernels (conv via the selected backend) vs the plain fp32 PyTorch modules."""
+    from coinstac_dinunet_b200.models import VBMNet
+    torch.manual_seed(3)
+    shape = (33, 34, 35)
+    ref = VBMNet(input_shape=shape).to(dev)
+    nat = VBMNet(input_shape=shape, native=True).to(dev)
+    nat.load_state_dict(ref.state_dict())
+    assert nat.is_native
+    x = torch.randn(4, 1, *shape, device=dev)
+    y = torch.randint(0, 2, (4,), device=dev)
+    out_ref, out_nat = ref(x), nat(x)
+    assert _rel(out_nat, out_ref) < 0.08
+    torch.nn.functional.cross_entropy(out_ref, y).backward()
+    torch.nn.functional.cross_entropy(out_nat, y).backward()
+    for (n1, p1), (_, p2) in zip(ref.named_parameters(), nat.named_parameters()):
+        assert p2.grad is not None and torch.isfinite(p2.grad).all(), n1
+        assert _rel(p2.grad, p1.grad) < 0.25, (n1, _rel(p2.grad, p1.grad))
+    for (n1, b1), (_, b2) in zip(ref.named_buffers(), nat.named_buffers()):
+        assert torch.allclose(b1.float(), b2.float(), rtol=5e-2, atol=5e-3), n1
+
+
+@pytest.mark.parametrize('cin,cout,shape', [(16, 32, (2, 7, 9, 11)), (32, 64, (1, 6, 5, 9)), (64, 128, (2, 4, 5, 6)),
+                                            (128, 256, (1, 3, 4, 3)), (32, 16, (1, 8, 8, 8)), (256, 128, (2, 3, 4, 3)),
+                                            (16, 32, (3, 20, 24, 20))])
+def test_tcgen05_conv3d_matches_torch(dev, cin, cout, shape):
+    from coinstac_dinunet_b200.ops.conv3d import conv3d_igemm_fwd, conv3d_igemm_bwd
+    torch.manual_seed(cin + cout)
+    N, D, H, W = shape
+    x = torch.randn(N, D, H, W, cin, device=dev).to(torch.bfloat16)
+    w = (torch.randn(cout, cin, 3, 3, 3, device=dev) * (27 * cin) ** -0.5)
+    y = conv3d_igemm_fwd(x, w)
+    x_ref = x.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    w_ref = w.to(torch.bfloat16).float().requires_grad_(True)
+    y_ref = torch.nn.functional.conv3d(x_ref, w_ref, padding=1)
+    assert _rel(y, _ndhwc(y_ref)) < 1e-2
+    dy = torch.randn_like(y_ref)
+    y_ref.backward(dy)
+    dx, dw = conv3d_igemm_bwd(_ndhwc(dy).to(torch.bfloat16), x, w, need_dx=True)
+    assert _rel(dx, _ndhwc(x_ref.grad)) < 1.5e-2
+    assert _rel(dw, w_ref.grad) < 1.5e-2
