@@ -1,0 +1,22 @@
+"""Conv3d weight gradient on the tcgen05 implicit-GEMM kernel (``csrc/conv3d_wgrad_tcgen05.cu``)."""
+import torch as _torch
+
+from . import native as _nat
+
+_SUPPORTED = {(16, 32), (32, 64), (64, 128), (128, 256), (32, 32), (64, 64)}
+
+
+def conv3d_wgrad(dy, x):
+    """dy: [N,D,H,W,Cout] bf16, x: [N,D,H,W,Cin] bf16 -> dW [Cout,Cin,3,3,3] fp32."""
+    N, D, H, W, cin = x.shape
+    cout = dy.shape[-1]
+    if (cin, cout) not in _SUPPORTED:
+        raise ImportError(f'no tcgen05 wgrad instantiation for {cin}->{cout}')
+    dwt = _torch.zeros((27 * cin, cout), dtype=_torch.float32, device=x.device)
+    code = _nat.lib().coinn_conv3d_wgrad(x.contiguous().data_ptr(), dy.contiguous().data_ptr(), dwt.data_ptr(),
+                                         N, D, H, W, cin, cout, _nat.stream_ptr(x.device))
+    _nat.check(code, f'coinn_conv3d_wgrad({cin}->{cout})')
+    from . import _count_launch
+    _count_launch()
+    # dwt[(kd,kh,kw,ci), co] -> [co, ci, kd, kh, kw]
+    return dwt.view(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2).contiguous()

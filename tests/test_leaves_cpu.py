@@ -1,0 +1,226 @@
+"""Unit tests of the leaf libraries: golden values from SURVEY §8.4, metric
+oracles from NumPy / scikit-learn, checkpoint layout (§5.4), arg-merge priority (local.py:93-109)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from coinstac_dinunet_b200 import COINNLocal, config
+from coinstac_dinunet_b200.config.keys import AGG_Engine, Key, Mode, Phase
+from coinstac_dinunet_b200.data import COINNPaddedDataSampler, datautils
+from coinstac_dinunet_b200.metrics import AUCROCMetrics, COINNAverages, ConfusionMatrix, Prf1a, dice_loss_binary
+from coinstac_dinunet_b200.utils import FrozenDict, lazy_debug, performance_improved_, save_cache, save_scores, stop_training_
+from coinstac_dinunet_b200.utils import tensorutils as tu
+
+
+def test_enums_are_wire_strings():
+    assert Phase.INIT_RUNS == 'init_runs' and json.dumps({'p': Phase.COMPUTATION}) == '{"p": "computation"}'
+    assert Mode.VALIDATION_WAITING == 'validation_waiting' and f'{AGG_Engine.dSGD}' == 'dSGD'
+    assert Key.TRAIN_SERIALIZABLE == 'serializable_train_scores'
+    assert config.grads_file == 'grads.npy' and config.avg_grads_file == 'avg_grads.npy'
+    assert config.boolean_string(' True ') and not config.boolean_string('no')
+
+
+def test_lazy_debug_cadence():
+    assert [x for x in range(1, 61) if lazy_debug(x)] == \
+        [1, 2, 4, 6, 9, 12, 15, 18, 20, 24, 28, 32, 36, 40, 44, 48, 52, 55, 60]
+
+
+def test_frozen_dict():
+    d = FrozenDict({'a': 1})
+    d['b'] = 2
+    d.update(c=3)
+    with pytest.raises(ValueError):
+        d['a'] = 5
+    with pytest.raises(ValueError):
+        d.update(b=0)
+    assert dict(d) == {'a': 1, 'b': 2, 'c': 3}
+
+
+def test_ratio_and_kfold_splits_golden(tmp_path):
+    files = [f'f{i}' for i in range(10)]
+    sp = datautils.create_ratio_split(list(files), {'split_ratio': [.6, .2, .2], 'split_dir': None}, shuffle_files=False)
+    assert sp == {'train': files[:6], 'validation': files[6:8], 'test': files[8:]}
+    sp = datautils.create_ratio_split(list(files), {'split_ratio': [.8, .2], 'split_dir': None}, shuffle_files=False)
+    assert sp == {'train': files[:8], 'test': files[8:]} and 'validation' not in sp
+    cache = {'num_folds': 5, 'split_dir': str(tmp_path)}
+    datautils.create_k_fold_splits(list(files), cache, shuffle_files=False)
+    s0 = json.load(open(tmp_path / 'SPLIT_0.json'))
+    s4 = json.load(open(tmp_path / 'SPLIT_4.json'))
+    assert s0 == {'train': files[4:], 'validation': ['f2', 'f3'], 'test': ['f0', 'f1']}
+    assert s4 == {'train': files[2:8], 'validation': ['f0', 'f1'], 'test': ['f8', 'f9']}
+    shuffled = list(files)
+    datautils._seeded_shuffle(shuffled)
+    assert shuffled == ['f5', 'f2', 'f7', 'f1', 'f8', 'f4', 'f3', 'f6', 'f0', 'f9']
+
+
+def test_init_k_folds_priority(tmp_path):
+    state = {'baseDirectory': str(tmp_path / 'in'), 'outputDirectory': str(tmp_path / 'out')}
+    os.makedirs(state['baseDirectory'])
+    cache = {'task_id': 't', 'num_folds': 3}
+    datautils.init_k_folds([f'f{i}' for i in range(9)], cache, state)
+    assert cache['splits'] == {'0': 'SPLIT_0.json', '1': 'SPLIT_1.json', '2': 'SPLIT_2.json'}
+    cache2 = {'task_id': 't2'}
+    datautils.init_k_folds([], cache2, state)
+    assert list(cache2['splits'].values()) == ['empty_split.json']
+
+
+def test_padded_sampler_golden():
+    assert list(COINNPaddedDataSampler(range(10), 4)) == [*range(10), 0, 1]
+    assert list(COINNPaddedDataSampler(range(3), 8)) == [0, 1, 2, 0, 1, 2, 0, 1]
+    s = COINNPaddedDataSampler(range(10), 4, seed=3, shuffle=True)
+    a = list(s)
+    s.set_epoch(1)
+    assert sorted(a[:10]) == list(range(10)) and len(a) == 12 and list(s) != a
+    assert len(COINNPaddedDataSampler(range(10), 4, drop_last=True)) == 8
+
+
+def test_model_selection_helpers():
+    cache = {'metric_direction': 'maximize', 'best_val_score': 0.5, 'best_val_epoch': 0, 'epochs': 10, 'patience': 2}
+    assert not performance_improved_(1, 0.50005, cache)
+    assert performance_improved_(2, 0.6, cache) and cache['best_val_epoch'] == 2
+    assert not stop_training_(4, cache) and stop_training_(5, cache)
+    cache = {'metric_direction': 'minimize', 'best_val_score': 1.0, 'best_val_epoch': 0, 'epochs': 3}
+    assert performance_improved_(1, 0.9, cache) and not performance_improved_(2, 0.95, cache)
+
+
+def test_averages():
+    a = COINNAverages(num_averages=2)
+    a.add(2.0, 4, 0); a.add(torch.tensor(1.0), 2, 0); a.add(3.0, 1, 1)
+    assert a.get().tolist() == [round(10 / 6, 5), 3.0]
+    b = COINNAverages(num_averages=2)
+    b.reduce_sites([a.serialize(), a.serialize()])
+    assert b.get().tolist() == a.get().tolist() and b.counts.tolist() == [12.0, 2.0]
+    assert COINNAverages().get().tolist() == [0.0]
+
+
+def test_prf1a_against_sklearn():
+    from sklearn import metrics as skm
+    g = torch.Generator().manual_seed(0)
+    pred, true = torch.randint(0, 2, (500,), generator=g), torch.randint(0, 2, (500,), generator=g)
+    m = Prf1a()
+    m.add(pred[:200], true[:200]); m.add(pred[200:] * 255, true[200:] * 255)   # 255 == 1
+    assert abs(m.precision - skm.precision_score(true, pred)) < 1e-4
+    assert abs(m.recall - skm.recall_score(true, pred)) < 1e-4
+    assert abs(m.f1 - skm.f1_score(true, pred)) < 1e-4
+    assert abs(m.accuracy - skm.accuracy_score(true, pred)) < 1e-4
+    assert abs(m.overlap - skm.jaccard_score(true, pred)) < 1e-4
+    assert m.tp + m.fp + m.tn + m.fn == 500
+    r = Prf1a()
+    r.reduce_sites([m.serialize(), [1.0, 1.0, 1.0]])
+    assert r.accuracy == round((m.accuracy + 1) / 2, 5) and r.extract('f1') > 0
+
+
+def test_confusion_matrix_and_remote_aggregation():
+    g = torch.Generator().manual_seed(1)
+    pred, true = torch.randint(0, 4, (300,), generator=g), torch.randint(0, 4, (300,), generator=g)
+    cm = ConfusionMatrix(num_classes=4)
+    cm.add(pred, true)
+    want = np.zeros((4, 4))
+    for p, t in zip(pred.tolist(), true.tolist()):
+        want[p, t] += 1
+    assert np.array_equal(cm.matrix.numpy(), want)
+    assert abs(cm.accuracy() - np.trace(want) / 300) < 1e-6
+    other = ConfusionMatrix(num_classes=4)
+    other.accumulate(cm); other.accumulate(cm)
+    assert other.get()[0] == cm.get()[0]
+    agg = ConfusionMatrix(num_classes=4)          # the reference breaks here
+    agg.reduce_sites([cm.serialize(), cm.serialize()])
+    assert agg.get() == cm.get()
+
+
+def test_auc_matches_sklearn_with_ties():
+    from sklearn import metrics as skm
+    g = torch.Generator().manual_seed(2)
+    prob = (torch.rand(400, generator=g) * 20).round() / 20      # many ties
+    lab = (torch.rand(400, generator=g) < prob * 0.7 + 0.1).long()
+    m = AUCROCMetrics()
+    m.add(prob[:100], lab[:100]); m.add(prob[100:], lab[100:])
+    assert abs(m.auc() - skm.roc_auc_score(lab.numpy(), prob.numpy())) < 1e-6
+    assert len(m.probabilities) == 400
+    r = AUCROCMetrics()
+    r.reduce_sites([[0.7], [0.9]])
+    assert r.get() == [0.8]
+
+
+def test_dice_loss():
+    o, t = torch.tensor([1., 1., 0., 0.]), torch.tensor([1., 0., 1., 0.])
+    assert abs(float(dice_loss_binary(o, t)) - (1 - (2 * 1 + 1) / (2 + 2 + 1))) < 1e-6
+    w = torch.tensor([0., 1., 1., 1.])
+    assert torch.isfinite(dice_loss_binary(o, t, beta=2, weights=w))
+
+
+def test_tensorutils_wire_format(tmp_path):
+    net = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.Linear(4, 4))
+    net(torch.randn(2, 4)).sum().backward()
+    grads = tu.extract_grads(net, 'float16')
+    path = tmp_path / 'grads.npy'
+    tu.save_arrays(str(path), grads)           # all leading dims equal: np.array(list) would fail/mis-shape
+    back = tu.load_arrays(str(path))
+    assert back.dtype == object and back.shape == (4,) and back[0].dtype == np.float16 and back[0].shape == (4, 4)
+    big, small = torch.zeros(1, 2, 10, 12), torch.ones(1, 3, 6, 8)
+    assert tu.safe_concat(big, small).shape == (1, 5, 6, 8)
+    assert tu.safe_concat(torch.zeros(1, 1, 8, 9, 10), torch.ones(1, 1, 4, 5, 6)).shape == (1, 2, 4, 5, 6)
+
+
+def test_save_scores_and_cache(tmp_path):
+    cache = {'log_header': 'Loss|Accuracy,F1', 'test_metrics': [[0.5, 0.9, 0.8]], 'obj': object(), 'n': {'t': torch.ones(1)}}
+    save_scores(cache, str(tmp_path), file_keys=['test_metrics'])
+    assert open(tmp_path / 'test_metrics.csv').read().split('\n')[:2] == ['Loss|Accuracy,F1', '0.5,0.9,0.8']
+    save_cache(cache, str(tmp_path))
+    assert json.load(open(tmp_path / 'logs.json'))['test_metrics'] == [[0.5, 0.9, 0.8]]
+
+
+def test_arg_merge_priority():
+    inp = {'task_id': 'tk', 'mode': 'train', 'batch_size': 3, 'agg_engine': 'powerSGD', 'num_folds': 2,
+           'tk_args': {'batch_size': 5, 'epochs': 7}, 'powerSGD_args': {'epochs': 9, 'rank': 2},
+           'tk_data_conf': {'epochs': 1, 'labels': 'l.csv'}}
+    cache = {}
+    COINNLocal(cache=cache, input=inp, state={}, learning_rate=0.5)
+    assert cache['batch_size'] == 5           # <task>_args beats plain input
+    assert cache['epochs'] == 9               # <engine>_args beats <task>_args
+    assert cache['labels'] == 'l.csv' and cache['rank'] == 2
+    assert cache['learning_rate'] == 0.5 and cache['validation_epochs'] == 1 and cache['patience'] == 31
+    cache2 = {}
+    with pytest.raises(AssertionError):
+        COINNLocal(cache=cache2, input={'task_id': 'x', 'mode': 'train'}, state={})     # no split info
+
+
+def test_checkpoint_layout_and_foreign_load(tmp_path):
+    from coinstac_dinunet_b200.models import FSVTrainer
+    from coinstac_dinunet_b200.distrib.nodes.remote import EmptyDataHandle
+    cache = {'mode': 'train', 'seed': 1, 'learning_rate': 1e-3, 'num_class': 2}
+    tr = FSVTrainer(data_handle=EmptyDataHandle(cache, {}, {}))
+    tr.init_nn(init_model=True, init_optim=True, set_devices=True, init_weights=True)
+    tr.nn['second'] = torch.nn.Linear(2, 2)
+    tr.save_checkpoint(str(tmp_path / 'c.pt'))
+    chk = torch.load(tmp_path / 'c.pt', weights_only=False)
+    assert chk['source'] == 'coinstac' and set(chk['models']) == {'fs_net', 'second'} and set(chk['optimizers']) == {'adam'}
+    before = tr.nn['fs_net'].classifier.weight.clone()
+    with torch.no_grad():
+        tr.nn['fs_net'].classifier.weight.zero_()
+    tr.load_checkpoint(str(tmp_path / 'c.pt'))
+    assert torch.equal(tr.nn['fs_net'].classifier.weight, before)
+    torch.save(tr.nn['fs_net'].state_dict(), tmp_path / 'raw.pt')       # foreign checkpoint = bare state_dict
+    tr.load_checkpoint(str(tmp_path / 'raw.pt'))
+
+
+def test_imageutils_and_plotter(tmp_path):
+    from coinstac_dinunet_b200.vision import imageutils as iu, plotter
+    idx = list(iu.get_chunk_indexes((10, 10), (4, 4), (3, 3)))
+    assert idx[0] == [0, 4, 0, 4] and idx[-1] == [6, 10, 6, 10] and len(idx) == 16   # last window repeats (as in the reference)
+    patches = np.stack([np.full((4, 4), 7, np.uint8)] * len(idx))
+    assert (iu.merge_patches(patches, (10, 10), (4, 4), (3, 3)) == 7).all()
+    a, b = np.array([[255, 0], [255, 0]]), np.array([[255, 255], [0, 0]])
+    assert iu.get_praf1(a, b) == {'Precision': 0.5, 'Recall': 0.5, 'Accuracy': 0.5, 'F1': 0.5}
+    assert iu.get_rgb_scores(a, b)[0, 0].tolist() == [255, 255, 255]
+    assert iu.get_pix_neigh(1, 1) == [(0, 1), (1, 2), (2, 1), (1, 0)] and len(iu.get_pix_neigh(1, 1, True)) == 8
+    assert iu.get_chunk_indices_by_index((10, 10), (4, 4), [(0, 0), (9, 9)]) == [[0, 4, 0, 4], [6, 10, 6, 10]]
+    assert iu.expand_and_mirror_patch((10, 10), [0, 4, 0, 4], (4, 4))[:4] == (0, 6, 0, 6)
+    blob = np.zeros((8, 8), np.uint8); blob[1:3, 1:3] = 1; blob[5:8, 4:8] = 1
+    assert iu.largest_cc(blob).sum() == 12
+    cache = {'log_header': 'Loss|Accuracy,F1', 'train_log': [[1.0, .5, .4], [.8, .6, .5], [.6, .7, .6]]}
+    plotter.plot_progress(cache, str(tmp_path), plot_keys=['train_log'])
+    assert any(f.startswith('train_log_0') for f in os.listdir(tmp_path))
