@@ -40,12 +40,18 @@ def pack_dgrad_weight(weight):
     return _pad_k(weight.detach().flip(2, 3, 4).permute(1, 2, 3, 4, 0).reshape(cin, 27 * cout).to(BF16))
 
 
-def _igemm(x, wk, kpad, cout):
+def conv_impl():
+    """'tma' (v2: im2col operand produced by 5-D TMA boxes) or 'gather' (v1: cp.async software gather)."""
+    import os
+    return os.environ.get('COINN_CONV_IMPL', 'tma')
+
+
+def _igemm(x, wk, kpad, cout, impl=None):
     N, D, H, W, cin = x.shape
     y = _torch.empty((N, D, H, W, cout), dtype=BF16, device=x.device)
-    code = _nat.lib().coinn_conv3d_igemm(x.data_ptr(), wk.data_ptr(), y.data_ptr(), N, D, H, W, cin, cout, kpad,
-                                         _nat.stream_ptr(x.device))
-    _nat.check(code, f'coinn_conv3d_igemm({cin}->{cout})')
+    fn = _nat.lib().coinn_conv3d_tma if (impl or conv_impl()) == 'tma' else _nat.lib().coinn_conv3d_igemm
+    code = fn(x.data_ptr(), wk.data_ptr(), y.data_ptr(), N, D, H, W, cin, cout, kpad, _nat.stream_ptr(x.device))
+    _nat.check(code, f'conv3d[{impl or conv_impl()}]({cin}->{cout})')
     _bump()
     return y
 

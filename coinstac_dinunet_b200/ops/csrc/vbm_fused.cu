@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const __nv_bfloat
 //   pass B: dy = gamma*invstd * (dz - dbeta/M - xhat * dgamma/M)     for ALL voxels (incl. odd borders)
 // ------------------------------------------------------------------------------------------------
 template <bool APPLY>
-__global__ void __launch_bounds__(256) bn_relu_pool_bwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dp,
+__global__ void __launch_bounds__(256, APPLY ? 1 : 2) bn_relu_pool_bwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dp,
                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                float* __restrict__ acc, __nv_bfloat16* __restrict__ dy,
@@ -250,16 +250,16 @@ __global__ void __launch_bounds__(256) bn_relu_pool_bwd_kernel(const __nv_bfloat
     const int my_cell_off = threadIdx.x / chunks;
     const long long total_cells = (long long)d.N * CD * CH * CW;
 
-    float sc[8], sh[8], gi[8], mu[8], is[8], db[8], dg[8], a_db[8], a_dg[8];
+    // per-channel constants of this thread's 8 channels
+    float sc[8], sh[8], mu[8], is[8], a0[8], a1[8];     // pass A: a0/a1 accumulate dbeta/dgamma; pass B: a0/a1 = dbeta/M, dgamma/M
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = my_chunk * 8 + j;
         mu[j] = mean[c]; is[j] = invstd[c];
         sc[j] = gamma[c] * is[j];
         sh[j] = beta[c] - mu[j] * sc[j];
-        gi[j] = sc[j];
-        a_db[j] = 0.f; a_dg[j] = 0.f;
-        if (APPLY) { db[j] = acc[c] * inv_count; dg[j] = acc[C + c] * inv_count; }
+        a0[j] = APPLY ? acc[c] * inv_count : 0.f;
+        a1[j] = APPLY ? acc[C + c] * inv_count : 0.f;
     }
     if (my_cell_off < cells_per_iter) {
         for (long long cell = (long long)blockIdx.x * cells_per_iter + my_cell_off; cell < total_cells;
@@ -270,59 +270,58 @@ __global__ void __launch_bounds__(256) bn_relu_pool_bwd_kernel(const __nv_bfloat
             const int pd = (int)(t % CD);
             const int n = (int)(t / CD);
             const bool pooled = pd < PD && ph < PH && pw < PW;
-            float g[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = 0.f;
+            if (!pooled && !APPLY) continue;             // no gradient flows through un-pooled borders
+            // issue all loads of the window first (8 x 16 B + dp), values stay packed as bf16
+            uint4 raw[8];
+            uint4 graw = make_uint4(0u, 0u, 0u, 0u);
             if (pooled) {
                 const long long pv = (((long long)n * PD + pd) * PH + ph) * PW + pw;
-                unpack8(ld_stream_u4(reinterpret_cast<const uint4*>(dp + pv * C) + my_chunk), g);
-            } else if (!APPLY) {
-                continue;                                // no gradient flows through un-pooled borders
+                graw = ld_stream_u4(reinterpret_cast<const uint4*>(dp + pv * C) + my_chunk);
             }
-            float yv[8][8];
-            float best[8]; int arg[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int zd = 2 * pd + (k >> 2), zh = 2 * ph + ((k >> 1) & 1), zw = 2 * pw + (k & 1);
+                raw[k] = make_uint4(0u, 0u, 0u, 0u);
                 if (zd < d.D && zh < d.H && zw < d.W) {
                     const long long vox = (((long long)n * d.D + zd) * d.H + zh) * d.W + zw;
-                    unpack8(ld_stream_u4(reinterpret_cast<const uint4*>(y + vox * C) + my_chunk), yv[k]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) yv[k][j] = 0.f;
+                    raw[k] = ld_stream_u4(reinterpret_cast<const uint4*>(y + vox * C) + my_chunk);
                 }
+            }
+            float g[8], best[8], besty[8];
+            int arg[8];
+            unpack8(graw, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; besty[j] = 0.f; arg[j] = 0; }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float f[8];
+                unpack8(raw[k], f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float z = fmaf(yv[k][j], sc[j], sh[j]);
-                    if (z > best[j]) { best[j] = z; arg[j] = k; }
+                    const float z = fmaf(f[j], sc[j], sh[j]);
+                    if (z > best[j]) { best[j] = z; besty[j] = f[j]; arg[j] = k; }      // first max wins (PyTorch rule)
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) if (!(best[j] > 0.f) || !pooled) g[j] = 0.f;   // relu'(<=0) = 0
+            for (int j = 0; j < 8; ++j) if (!(best[j] > 0.f) || !pooled) g[j] = 0.f;       // relu'(<=0) = 0
             if (!APPLY) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float xh = (yv[0][j] - mu[j]) * is[j];     // placeholder, replaced below per arg
-                    (void)xh;
+                    a0[j] += g[j];
+                    a1[j] = fmaf(g[j], (besty[j] - mu[j]) * is[j], a1[j]);
                 }
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (arg[j] == k) { a_db[j] += g[j]; a_dg[j] = fmaf(g[j], (yv[k][j] - mu[j]) * is[j], a_dg[j]); }
             } else {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int zd = 2 * pd + (k >> 2), zh = 2 * ph + ((k >> 1) & 1), zw = 2 * pw + (k & 1);
                     if (!(zd < d.D && zh < d.H && zw < d.W)) continue;
-                    float o[8];
+                    float f[8], o[8];
+                    unpack8(raw[k], f);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float dz = (arg[j] == k) ? g[j] : 0.f;
-                        const float xh = (yv[k][j] - mu[j]) * is[j];
-                        o[j] = gi[j] * (dz - db[j] - xh * dg[j]);
+                        const float xh = (f[j] - mu[j]) * is[j];
+                        o[j] = sc[j] * (dz - a0[j] - xh * a1[j]);
                     }
                     const long long vox = (((long long)n * d.D + zd) * d.H + zh) * d.W + zw;
                     reinterpret_cast<uint4*>(dy + vox * C)[my_chunk] = pack8(o);
@@ -333,8 +332,8 @@ __global__ void __launch_bounds__(256) bn_relu_pool_bwd_kernel(const __nv_bfloat
     if (!APPLY) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            atomicAdd(&sm[my_chunk * 8 + j], a_db[j]);
-            atomicAdd(&sm[C + my_chunk * 8 + j], a_dg[j]);
+            atomicAdd(&sm[my_chunk * 8 + j], a0[j]);
+            atomicAdd(&sm[C + my_chunk * 8 + j], a1[j]);
         }
         __syncthreads();
         for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&acc[i], sm[i]);

@@ -254,9 +254,12 @@ def test_native_vbmnet_matches_torch_reference(dev):
 
 @pytest.mark.parametrize('cin,cout,shape', [(16, 32, (2, 7, 9, 11)), (32, 64, (1, 6, 5, 9)), (64, 128, (2, 4, 5, 6)),
                                             (128, 256, (1, 3, 4, 3)), (32, 16, (1, 8, 8, 8)), (256, 128, (2, 3, 4, 3)),
-                                            (16, 32, (3, 20, 24, 20))])
-def test_tcgen05_conv3d_matches_torch(dev, cin, cout, shape):
+                                            (16, 32, (3, 20, 24, 20)), (16, 32, (1, 5, 7, 60)),
+                                            (64, 32, (1, 4, 9, 7))])
+@pytest.mark.parametrize('impl', ['tma', 'gather'])
+def test_tcgen05_conv3d_matches_torch(dev, cin, cout, shape, impl, monkeypatch):
     from coinstac_dinunet_b200.ops.conv3d import conv3d_igemm_fwd, conv3d_igemm_bwd
+    monkeypatch.setenv('COINN_CONV_IMPL', impl)
     torch.manual_seed(cin + cout)
     N, D, H, W = shape
     x = torch.randn(N, D, H, W, cin, device=dev).to(torch.bfloat16)
