@@ -41,17 +41,31 @@ def pack_dgrad_weight(weight):
 
 
 def conv_impl():
-    """'tma' (v2: im2col operand produced by 5-D TMA boxes) or 'gather' (v1: cp.async software gather)."""
+    """'auto' (default): halo kernel (v3, every input voxel crosses L2->SM once) where it applies, else the
+    TMA-box kernel (v2).  'halo' / 'tma' / 'gather' force one implementation ('gather' = v1, cp.async)."""
     import os
-    return os.environ.get('COINN_CONV_IMPL', 'tma')
+    return os.environ.get('COINN_CONV_IMPL', 'auto')
+
+
+#: which implementation served the last call (tests / profiling)
+last_impl = None
 
 
 def _igemm(x, wk, kpad, cout, impl=None):
+    global last_impl
     N, D, H, W, cin = x.shape
     y = _torch.empty((N, D, H, W, cout), dtype=BF16, device=x.device)
-    fn = _nat.lib().coinn_conv3d_tma if (impl or conv_impl()) == 'tma' else _nat.lib().coinn_conv3d_igemm
-    code = fn(x.data_ptr(), wk.data_ptr(), y.data_ptr(), N, D, H, W, cin, cout, kpad, _nat.stream_ptr(x.device))
-    _nat.check(code, f'conv3d[{impl or conv_impl()}]({cin}->{cout})')
+    impl = impl or conv_impl()
+    lib = _nat.lib()
+    args = (x.data_ptr(), wk.data_ptr(), y.data_ptr(), N, D, H, W, cin, cout, kpad, _nat.stream_ptr(x.device))
+    code = -1
+    if impl in ('auto', 'halo'):
+        code, last_impl = lib.coinn_conv3d_halo(*args), 'halo'
+    if code == -1 and impl != 'gather':
+        code, last_impl = lib.coinn_conv3d_tma(*args), 'tma'
+    if code == -1:
+        code, last_impl = lib.coinn_conv3d_igemm(*args), 'gather'
+    _nat.check(code, f'conv3d[{last_impl}]({cin}->{cout})')
     _bump()
     return y
 

@@ -1,0 +1,230 @@
+// Conv3d (3x3x3, pad 1, stride 1) fprop / dgrad, version 3 ("halo"): every input voxel crosses L2 -> SM once.
+//
+// v2 (conv3d_tma.cu) loads one shifted 128-pixel box per filter tap: 27x redundant L2 traffic, which is what
+// bounds it (profiles/: ~5 TB/s of L2->SM traffic).  Here a tile is TH complete rows of one (n, d) plane and the
+// TMA unit materialises the zero-PADDED halo  (TH+2) x (W+2) pixels x 8 channels  per (d-plane, channel chunk)
+// directly in shared memory (out-of-bounds coordinates are zero filled).  In that padded, flattened layout the
+// operand of tap (kd,kh,kw) is the SAME buffer shifted by (kh*(W+2) + kw) pixels, i.e. 27 (x CIN/16) tcgen05.mma
+// instructions read 27 different start addresses of one halo - no im2col is ever built.  Layout: K-major,
+// no swizzle; a pixel's 8-channel chunk is 16 bytes, 8 consecutive pixels form one 128-byte core matrix
+// (SBO = 128 B), the second chunk of a K=16 step lives one region further (LBO = region stride).
+// The 27*CIN x COUT weight matrix is loaded once per (persistent) CTA and stays in shared memory.
+// Output rows at the two padding columns of every line are computed and discarded (2/(W+2) waste).
+#include "umma.cuh"
+
+namespace coinn {
+
+constexpr int CH_THREADS = 192;
+
+struct ConvHaloParams {
+    __nv_bfloat16* y;           // [N, D, H, W, COUT]
+    int N, D, H, W;
+    int TH, Wp;                 // rows per tile, padded width (W + 2); TH * Wp <= 128
+    int tiles_h, num_tiles;
+    uint32_t region_bytes;      // (TH+2) * Wp * 16, rounded up to 128
+    uint32_t region_tx;         // exact bytes one halo box delivers
+    int stages;
+};
+
+__device__ __forceinline__ void tma_load_5d_h(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                              int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(CH_THREADS, 1)
+conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const ConvHaloParams p) {
+    constexpr int CHUNKS = CIN / 8;                         // 16-byte channel chunks per pixel
+    constexpr int REGIONS = 3 * CHUNKS;                     // per tile: (d-plane, chunk)
+    constexpr int KCH = 27 * CHUNKS;                        // weight k-chunks
+    constexpr uint32_t W_CHUNK_BYTES = COUT * 16;
+    constexpr uint32_t W_BYTES = (KCH * W_CHUNK_BYTES + 1023) / 1024 * 1024;
+    constexpr uint32_t TMEM_COLS = (2 * COUT) < 32 ? 32 : 2 * COUT;
+    constexpr int MAX_STAGES = 8;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w_smem = smem;
+    uint8_t* stage_base = smem + W_BYTES;
+    const uint32_t stage_bytes = REGIONS * p.region_bytes + 1024;       // + slack: shifted reads run past the last region
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + (size_t)p.stages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + MAX_STAGES;
+    uint64_t* tmem_full = bars + 2 * MAX_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint64_t* w_bar = tmem_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int STAGES = p.stages;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_w);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        mbar_init(w_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tcgen05_before_sync();
+    __syncthreads();
+    tcgen05_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const int first_tile = blockIdx.x, tile_step = gridDim.x;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // weights: one [COUT x 8] box per k-chunk, resident for the lifetime of the CTA
+            mbar_arrive_expect_tx(w_bar, KCH * W_CHUNK_BYTES);
+            for (int kc = 0; kc < KCH; ++kc) tma_load_2d(w_smem + kc * W_CHUNK_BYTES, &tmap_w, w_bar, kc * 8, 0);
+            uint32_t it = 0;
+            for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++it) {
+                const int plane = tile / p.tiles_h, h0 = (tile % p.tiles_h) * p.TH;
+                const int n = plane / p.D, d = plane % p.D;
+                const int s = it % STAGES;
+                mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                uint8_t* dst = stage_base + (size_t)s * stage_bytes;
+                mbar_arrive_expect_tx(&full_bar[s], REGIONS * p.region_tx);
+#pragma unroll
+                for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+                    for (int c = 0; c < CHUNKS; ++c)
+                        tma_load_5d_h(dst + (kd * CHUNKS + c) * p.region_bytes, &tmap_x, &full_bar[s], c * 8, -1, h0 - 1, d + kd - 1, n);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(128, COUT, 1, 0, 0);
+            mbar_wait(w_bar, 0);
+            const uint32_t w_addr = smem_u32(w_smem);
+            uint32_t it = 0;
+            for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++it) {
+                const uint32_t a = it & 1;
+                const int s = it % STAGES;
+                mbar_wait(&tmem_empty[a], ((it >> 1) & 1) ^ 1);
+                mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                tcgen05_after_sync();
+                const uint32_t d_tmem = tmem_base + a * COUT;
+                const uint32_t halo = smem_u32(stage_base + (size_t)s * stage_bytes);
+                uint32_t first = 1;
+#pragma unroll 1
+                for (int tap = 0; tap < 27; ++tap) {
+                    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+                    const uint32_t shift = (uint32_t)(kh * p.Wp + kw) * 16u;
+#pragma unroll
+                    for (int j = 0; j < CIN / 16; ++j) {
+                        const uint64_t adesc = make_smem_desc(halo + (kd * CHUNKS + 2 * j) * p.region_bytes + shift,
+                                                              p.region_bytes, 128, SMEM_LAYOUT_NONE);
+                        const uint64_t bdesc = make_smem_desc(w_addr + (tap * CHUNKS + 2 * j) * W_CHUNK_BYTES,
+                                                              W_CHUNK_BYTES, 128, SMEM_LAYOUT_NONE);
+                        umma_f16(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
+                        first = 0;
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+                umma_commit(&tmem_full[a]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int pix = q * 32 + lane;
+        const int hh = pix / p.Wp, ww = pix % p.Wp;
+        uint32_t it = 0;
+        for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++it) {
+            const uint32_t a = it & 1;
+            const int plane = tile / p.tiles_h, h = (tile % p.tiles_h) * p.TH + hh;
+            const bool ok = hh < p.TH && ww < p.W && h < p.H;
+            __nv_bfloat16* out = p.y + (((long long)plane * p.H + h) * p.W + ww) * COUT;
+            mbar_wait(&tmem_full[a], (it >> 1) & 1);
+            tcgen05_after_sync();
+#pragma unroll 1
+            for (int c = 0; c < COUT; c += 16) {
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + a * COUT + c, r);
+                tmem_ld_wait();
+                if (ok) {
+                    uint4 lo = make_uint4(pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1])),
+                                          pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3])),
+                                          pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5])),
+                                          pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7])));
+                    uint4 hi = make_uint4(pack_bf16x2(__uint_as_float(r[8]), __uint_as_float(r[9])),
+                                          pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11])),
+                                          pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13])),
+                                          pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15])));
+                    *reinterpret_cast<uint4*>(out + c) = lo;
+                    *reinterpret_cast<uint4*>(out + c + 8) = hi;
+                }
+            }
+            tcgen05_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[a]);
+        }
+    }
+
+    tcgen05_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int CIN, int COUT>
+static int launch_conv_halo(const void* x, const void* wk, void* y, int N, int D, int H, int W, int kpad, cudaStream_t st) {
+    constexpr int CHUNKS = CIN / 8, REGIONS = 3 * CHUNKS, KCH = 27 * CHUNKS;
+    constexpr uint32_t W_BYTES = (KCH * COUT * 16 + 1023) / 1024 * 1024;
+    ConvHaloParams p;
+    p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    p.N = N; p.D = D; p.H = H; p.W = W;
+    p.Wp = W + 2;
+    if (p.Wp > 128) return -1;
+    p.TH = 128 / p.Wp;
+    if (p.TH > H) p.TH = H;
+    if (p.TH + 2 > 256) return -1;
+    p.tiles_h = (H + p.TH - 1) / p.TH;
+    p.num_tiles = N * D * p.tiles_h;
+    p.region_tx = (uint32_t)(p.TH + 2) * p.Wp * 16u;
+    p.region_bytes = (p.region_tx + 127u) & ~127u;
+    const uint32_t stage_bytes = REGIONS * p.region_bytes + 1024;
+    const int budget = 220 * 1024 - (int)W_BYTES - 1024 - 512;
+    int stages = budget / (int)stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return -1;
+    p.stages = stages;
+    const int smem_bytes = (int)W_BYTES + stages * (int)stage_bytes + 1024 + 512;
+
+    auto enc = get_tensor_map_encoder();
+    if (!enc) return -2;
+    CUtensorMap tx, tw;
+    {
+        cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+        cuuint64_t strides[4] = {(cuuint64_t)CIN * 2, (cuuint64_t)W * CIN * 2, (cuuint64_t)H * W * CIN * 2, (cuuint64_t)D * H * W * CIN * 2};
+        cuuint32_t box[5] = {8, (cuuint32_t)p.Wp, (cuuint32_t)(p.TH + 2), 1, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        if (enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return -3;
+    }
+    if (make_tmap_2d_bf16(&tw, wk, (uint64_t)COUT, (uint64_t)kpad, (uint64_t)kpad * 2, COUT, 8, CU_TENSOR_MAP_SWIZZLE_NONE) != 0) return -4;
+    static int configured = 0;
+    if (configured < smem_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(conv3d_halo_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem_bytes;
+    }
+    const int grid = p.num_tiles < B200_SM_COUNT ? p.num_tiles : B200_SM_COUNT;
+    conv3d_halo_kernel<CIN, COUT><<<grid, CH_THREADS, smem_bytes, st>>>(tx, tw, p);
+    COINN_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace coinn
+
+// same contract as coinn_conv3d_igemm; returns -1 when the shape is outside what the halo kernel covers
+COINN_API int coinn_conv3d_halo(const void* x, const void* wk, void* y, int N, int D, int H, int W, int cin, int cout,
+                                int kpad, void* stream) {
+    using namespace coinn;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define CASE(CI, CO) if (cin == CI && cout == CO) return launch_conv_halo<CI, CO>(x, wk, y, N, D, H, W, kpad, st);
+    CASE(16, 32) CASE(32, 16) CASE(32, 64) CASE(64, 32) CASE(16, 16) CASE(32, 32)
+#undef CASE
+    return -1;
+}

@@ -40,7 +40,7 @@ template <> __device__ __forceinline__ float load_in<float>(const float* p) { re
 template <> __device__ __forceinline__ float load_in<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
 template <typename TIn>
-__global__ void __launch_bounds__(256) conv1_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ w /*[16][27]*/,
+__global__ void __launch_bounds__(256, 1) conv1_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ w /*[16][27]*/,
                                                         __nv_bfloat16* __restrict__ y, float* __restrict__ stats, Dims d) {
     __shared__ float4 ws[27][4];              // [tap][co/4] -> 4 consecutive output channels
     __shared__ float red[2 * C1_OUT];
@@ -71,35 +71,38 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const TIn* __restrict__ 
 #pragma unroll
             for (int c = 0; c < C1_OUT; ++c) acc[v][c] = 0.f;
 
+        // all 9 x (VOX+2) neighbourhood values first (branch-free: clamped address x validity), so the loads
+        // are in flight together and the 27 x 64 FMAs below run without further memory stalls
+        float in[9][C1_VOX + 2];
 #pragma unroll
-        for (int kd = 0; kd < 3; ++kd) {
-            const int zd = dd + kd - 1;
-            if (zd < 0 || zd >= d.D) continue;
+        for (int r = 0; r < 9; ++r) {
+            const int zd = dd + r / 3 - 1, zh = h + r % 3 - 1;
+            const bool row_ok = zd >= 0 && zd < d.D && zh >= 0 && zh < d.H;
+            const int cd = min(max(zd, 0), d.D - 1), chh = min(max(zh, 0), d.H - 1);
+            const TIn* row = x + (((long long)n * d.D + cd) * d.H + chh) * d.W;
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-                const int zh = h + kh - 1;
-                if (zh < 0 || zh >= d.H) continue;
-                const TIn* row = x + (((long long)n * d.D + zd) * d.H + zh) * d.W;
-                float in[C1_VOX + 2];
+            for (int j = 0; j < C1_VOX + 2; ++j) {
+                const int zw = w0 + j - 1;
+                const int cw = min(max(zw, 0), d.W - 1);
+                const float v = load_in<TIn>(row + cw);
+                in[r][j] = (row_ok && zw >= 0 && zw < d.W) ? v : 0.f;
+            }
+        }
 #pragma unroll
-                for (int j = 0; j < C1_VOX + 2; ++j) {
-                    const int zw = w0 + j - 1;
-                    in[j] = (zw >= 0 && zw < d.W) ? load_in<TIn>(row + zw) : 0.f;
-                }
+        for (int r = 0; r < 9; ++r) {
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const int tap = (kd * 3 + kh) * 3 + kw;
+            for (int kw = 0; kw < 3; ++kw) {
+                const int tap = r * 3 + kw;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 wv = ws[tap][q];
+                for (int q = 0; q < 4; ++q) {
+                    const float4 wv = ws[tap][q];
 #pragma unroll
-                        for (int v = 0; v < C1_VOX; ++v) {
-                            const float xv = in[v + kw];
-                            acc[v][4 * q + 0] = fmaf(xv, wv.x, acc[v][4 * q + 0]);
-                            acc[v][4 * q + 1] = fmaf(xv, wv.y, acc[v][4 * q + 1]);
-                            acc[v][4 * q + 2] = fmaf(xv, wv.z, acc[v][4 * q + 2]);
-                            acc[v][4 * q + 3] = fmaf(xv, wv.w, acc[v][4 * q + 3]);
-                        }
+                    for (int v = 0; v < C1_VOX; ++v) {
+                        const float xv = in[r][v + kw];
+                        acc[v][4 * q + 0] = fmaf(xv, wv.x, acc[v][4 * q + 0]);
+                        acc[v][4 * q + 1] = fmaf(xv, wv.y, acc[v][4 * q + 1]);
+                        acc[v][4 * q + 2] = fmaf(xv, wv.z, acc[v][4 * q + 2]);
+                        acc[v][4 * q + 3] = fmaf(xv, wv.w, acc[v][4 * q + 3]);
                     }
                 }
             }
@@ -347,10 +350,10 @@ __global__ void __launch_bounds__(256, APPLY ? 1 : 2) bn_relu_pool_bwd_kernel(co
 constexpr int WG_TILE_W = 64;            // voxels (along w) staged per step
 
 template <typename TIn>
-__global__ void __launch_bounds__(256) conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x,
+__global__ void __launch_bounds__(128) conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x,
                                                           float* __restrict__ dw /*[16][27]*/, Dims d) {
-    __shared__ __align__(16) __nv_bfloat16 s_dy[8][WG_TILE_W][C1_OUT];     // per warp
-    __shared__ float s_x[8][3][3][WG_TILE_W + 2];                          // per warp: halo rows
+    __shared__ __align__(16) float s_dy[4][WG_TILE_W][C1_OUT];             // per warp, already fp32
+    __shared__ float s_x[4][3][3][WG_TILE_W + 2];                          // per warp: halo rows
     __shared__ float s_acc[C1_OUT * 27];
     for (int i = threadIdx.x; i < C1_OUT * 27; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
@@ -373,30 +376,39 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const __nv_bfloat16* _
         const int w0 = wt * WG_TILE_W;
         const int nw = min(WG_TILE_W, d.W - w0);
         __syncwarp();
-        // stage dy rows (nw voxels x 32 bytes) and the 3x3 halo rows of x
+        // stage dy rows (nw voxels x 16 ch) as fp32 and the 3x3 halo rows of x
         const uint4* src = reinterpret_cast<const uint4*>(dy + ((((long long)n * d.D + dd) * d.H + h) * d.W + w0) * C1_OUT);
-        for (int i = lane; i < nw * 2; i += 32) reinterpret_cast<uint4*>(&s_dy[warp][0][0])[i] = ld_stream_u4(src + i);
+        for (int i = lane; i < nw * 2; i += 32) {
+            float f[8];
+            unpack8(ld_stream_u4(src + i), f);
+            float4* dst = reinterpret_cast<float4*>(&s_dy[warp][0][0]) + i * 2;
+            dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+            dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+        }
         for (int r = 0; r < 9; ++r) {
             const int zd = dd + r / 3 - 1, zh = h + r % 3 - 1;
             const bool ok = zd >= 0 && zd < d.D && zh >= 0 && zh < d.H;
-            const TIn* row = x + (((long long)n * d.D + zd) * d.H + zh) * d.W;
+            const TIn* row = x + (((long long)n * d.D + (ok ? zd : 0)) * d.H + (ok ? zh : 0)) * d.W;
             for (int j = lane; j < nw + 2; j += 32) {
                 const int zw = w0 + j - 1;
                 s_x[warp][r / 3][r % 3][j] = (ok && zw >= 0 && zw < d.W) ? load_in<TIn>(row + zw) : 0.f;
             }
         }
         __syncwarp();
+        const float* xs = &s_x[warp][kd][kh][kw];
+#pragma unroll 4
         for (int v = 0; v < nw; ++v) {
-            const float xv = s_x[warp][kd][kh][v + kw];
-            const uint4 lo = reinterpret_cast<const uint4*>(&s_dy[warp][v][0])[0];
-            const uint4 hi = reinterpret_cast<const uint4*>(&s_dy[warp][v][0])[1];
-            float g[8];
-            unpack8(lo, g);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[c] = fmaf(g[c], xv, acc[c]);
-            unpack8(hi, g);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[8 + c] = fmaf(g[c], xv, acc[8 + c]);
+            const float xv = xs[v];
+            const float4* g = reinterpret_cast<const float4*>(&s_dy[warp][v][0]);   // same address for all lanes: broadcast
+            const float4 g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3];
+            acc[0] = fmaf(g0.x, xv, acc[0]);   acc[1] = fmaf(g0.y, xv, acc[1]);
+            acc[2] = fmaf(g0.z, xv, acc[2]);   acc[3] = fmaf(g0.w, xv, acc[3]);
+            acc[4] = fmaf(g1.x, xv, acc[4]);   acc[5] = fmaf(g1.y, xv, acc[5]);
+            acc[6] = fmaf(g1.z, xv, acc[6]);   acc[7] = fmaf(g1.w, xv, acc[7]);
+            acc[8] = fmaf(g2.x, xv, acc[8]);   acc[9] = fmaf(g2.y, xv, acc[9]);
+            acc[10] = fmaf(g2.z, xv, acc[10]); acc[11] = fmaf(g2.w, xv, acc[11]);
+            acc[12] = fmaf(g3.x, xv, acc[12]); acc[13] = fmaf(g3.y, xv, acc[13]);
+            acc[14] = fmaf(g3.z, xv, acc[14]); acc[15] = fmaf(g3.w, xv, acc[15]);
         }
     }
     if (lane < 27) {
@@ -425,8 +437,8 @@ COINN_API int coinn_conv1_fwd(const void* x, int x_dtype, const float* w, void* 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long groups = (long long)N * D * H * ((W + C1_VOX - 1) / C1_VOX);
     const int grid = grid_for(groups, 256, 2);
-    if (x_dtype == 0) conv1_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, w, (__nv_bfloat16*)y, stats, d);
-    else conv1_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, stats, d);
+    if (x_dtype != 0) return (int)cudaErrorInvalidValue;       // callers up-cast bf16 volumes (8.5 MB) first
+    conv1_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, w, (__nv_bfloat16*)y, stats, d);
     COINN_CHECK_LAUNCH();
     return 0;
 }
@@ -491,10 +503,10 @@ COINN_API int coinn_conv1_wgrad(const void* dy, const void* x, int x_dtype, floa
     Dims d{N, D, H, W};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long jobs = (long long)N * D * H * ((W + WG_TILE_W - 1) / WG_TILE_W);
-    long long want = (jobs + 8 * 4 - 1) / (8 * 4);
-    const int grid = (int)(want < 1 ? 1 : (want > 4LL * B200_SM_COUNT ? 4LL * B200_SM_COUNT : want));
-    if (x_dtype == 0) conv1_wgrad_kernel<float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const float*)x, dw, d);
-    else conv1_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, d);
+    long long want = (jobs + 4 * 4 - 1) / (4 * 4);
+    const int grid = (int)(want < 1 ? 1 : (want > 8LL * B200_SM_COUNT ? 8LL * B200_SM_COUNT : want));
+    if (x_dtype == 0) conv1_wgrad_kernel<float><<<grid, 128, 0, st>>>((const __nv_bfloat16*)dy, (const float*)x, dw, d);
+    else conv1_wgrad_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, d);
     COINN_CHECK_LAUNCH();
     return 0;
 }

@@ -34,11 +34,11 @@ def _chk(code, what):
 def conv1_fwd(x, weight):
     """x: [N,D,H,W] fp32/bf16 (single channel), weight: [16,1,3,3,3] -> (y [N,D,H,W,16] bf16, stats[32])."""
     N, D, H, W = x.shape
-    x = x.contiguous()
+    x = x.float().contiguous()
     w = weight.detach().float().reshape(16, 27).contiguous()
     y = _torch.empty((N, D, H, W, 16), dtype=BF16, device=x.device)
     stats = _torch.zeros(32, dtype=_torch.float32, device=x.device)
-    _chk(_nat.lib().coinn_conv1_fwd(x.data_ptr(), 0 if x.dtype == _torch.float32 else 1, w.data_ptr(), y.data_ptr(),
+    _chk(_nat.lib().coinn_conv1_fwd(x.data_ptr(), 0, w.data_ptr(), y.data_ptr(),
                                     stats.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_fwd')
     _bump()
     return y, stats

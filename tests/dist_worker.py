@@ -47,11 +47,10 @@ if __name__ == '__main__':
     opts = dict(kv.split('=', 1) for kv in sys.argv[3:])
     from coinstac_dinunet_b200.engine import init_process_group
     init_process_group()
-    try:
-        from tests import dist_scenarios_gpu  # noqa: F401  (registers GPU scenarios when present)
+    if torch.cuda.is_available():
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import dist_scenarios_gpu  # registers the GPU scenarios
         SCENARIOS.update(dist_scenarios_gpu.SCENARIOS)
-    except Exception:
-        pass
     SCENARIOS[name](work, opts)
     dist.barrier()
     dist.destroy_process_group()

@@ -256,7 +256,7 @@ def test_native_vbmnet_matches_torch_reference(dev):
                                             (128, 256, (1, 3, 4, 3)), (32, 16, (1, 8, 8, 8)), (256, 128, (2, 3, 4, 3)),
                                             (16, 32, (3, 20, 24, 20)), (16, 32, (1, 5, 7, 60)),
                                             (64, 32, (1, 4, 9, 7))])
-@pytest.mark.parametrize('impl', ['tma', 'gather'])
+@pytest.mark.parametrize('impl', ['halo', 'tma', 'gather'])
 def test_tcgen05_conv3d_matches_torch(dev, cin, cout, shape, impl, monkeypatch):
     from coinstac_dinunet_b200.ops.conv3d import conv3d_igemm_fwd, conv3d_igemm_bwd
     monkeypatch.setenv('COINN_CONV_IMPL', impl)
