@@ -76,8 +76,33 @@ class NvlinkLearner(COINNLearner):
             out.update(**flags)
         return its, out
 
+    def _graphed_round(self, steps):
+        """``cache['cuda_graph']``: capture the whole step once, then replay it ``steps`` times."""
+        from .graph_step import GraphedStep
+        gs = self.cache.get('_graph_step')
+        done = 0
+        if gs is None or gs.arena is not self.arena:
+            batch, _ = self.trainer.data_handle.next_iter()
+            gs = self.cache['_graph_step'] = GraphedStep(self).capture(batch)
+            done = 0                                  # capture consumed one batch but its steps were warm-up
+        for _ in range(steps - done):
+            batch, _ = self.trainer.data_handle.next_iter()
+            gs.step(batch)
+            if self.cache.get('readback_per_step'):
+                self.cache['last_loss'] = float(gs.it['loss'].detach())
+        avg, met = gs.drain()
+        return {'averages': avg, 'metrics': met}
+
     def to_reduce(self):
         its, out = [], {}
+        graphable = (self.cache.get('cuda_graph') and self.device.type == 'cuda'
+                     and self.cache.get('local_iterations', 1) == 1 and self.arena.backend == 'nvlink')
+        if graphable:
+            it = self._graphed_round(self._steps_this_round())
+            self.cache['cursor'] = 0
+            out['mode'] = Mode.VALIDATION_WAITING
+            out['fused_steps'] = self.arena.steps_done
+            return it, out
         for _ in range(self._steps_this_round()):
             step_its, flags = self.backward()
             self.arena.reduce_and_step()

@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+timeout -s KILL 400 python -m pytest tests/test_ops_gpu.py -q -k "conv or bn_relu or native_vbm" > gpurun_out/pytest_conv3.log 2>&1; echo "conv rc=$?"
+grep -E "passed|failed|Error|assert|FAILED" gpurun_out/pytest_conv3.log | head -30
+timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --skip-e2e > gpurun_out/bench_halo.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_halo.log | cut -c1-220
+timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 600 --csv --log-file gpurun_out/launches_halo.csv python bench.py --steps 2 --warmup 1 --skip-e2e > gpurun_out/ncu_bench5.log 2>&1; echo "ncu rc=$?"
+python scripts/summarize_launches.py gpurun_out/launches_halo.csv 22
