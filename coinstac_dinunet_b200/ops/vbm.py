@@ -31,25 +31,40 @@ def _chk(code, what):
 
 
 # ------------------------------------------------------------------------------------ kernels
-def conv1_fwd(x, weight):
+def conv1_impl():
+    """'tc' (default): tcgen05 kernels of conv1_tc.cu; 'cuda': the CUDA-core kernels of vbm_fused.cu."""
+    import os
+    return os.environ.get('COINN_CONV1_IMPL', 'tc')
+
+
+def conv1_fwd(x, weight, impl=None):
     """x: [N,D,H,W] fp32/bf16 (single channel), weight: [16,1,3,3,3] -> (y [N,D,H,W,16] bf16, stats[32])."""
     N, D, H, W = x.shape
     x = x.float().contiguous()
     w = weight.detach().float().reshape(16, 27).contiguous()
     y = _torch.empty((N, D, H, W, 16), dtype=BF16, device=x.device)
     stats = _torch.zeros(32, dtype=_torch.float32, device=x.device)
-    _chk(_nat.lib().coinn_conv1_fwd(x.data_ptr(), 0, w.data_ptr(), y.data_ptr(),
-                                    stats.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_fwd')
+    if (impl or conv1_impl()) == 'tc':
+        _chk(_nat.lib().coinn_conv1_fwd_tc(x.data_ptr(), w.data_ptr(), y.data_ptr(), stats.data_ptr(), N, D, H, W,
+                                           _sp(x)), 'coinn_conv1_fwd_tc')
+    else:
+        _chk(_nat.lib().coinn_conv1_fwd(x.data_ptr(), 0, w.data_ptr(), y.data_ptr(),
+                                        stats.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_fwd')
     _bump()
     return y, stats
 
 
-def conv1_wgrad(dy, x):
+def conv1_wgrad(dy, x, impl=None):
     """dy: [N,D,H,W,16] bf16, x: [N,D,H,W] -> dW [16,1,3,3,3] fp32."""
     N, D, H, W = x.shape
     dw = _torch.zeros(16 * 27, dtype=_torch.float32, device=x.device)
-    _chk(_nat.lib().coinn_conv1_wgrad(dy.data_ptr(), x.data_ptr(), 0 if x.dtype == _torch.float32 else 1,
-                                      dw.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_wgrad')
+    if (impl or conv1_impl()) == 'tc':
+        x = x.float().contiguous()
+        _chk(_nat.lib().coinn_conv1_wgrad_tc(dy.contiguous().data_ptr(), x.data_ptr(), dw.data_ptr(), N, D, H, W,
+                                             _sp(x)), 'coinn_conv1_wgrad_tc')
+    else:
+        _chk(_nat.lib().coinn_conv1_wgrad(dy.data_ptr(), x.data_ptr(), 0 if x.dtype == _torch.float32 else 1,
+                                          dw.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_wgrad')
     _bump()
     return dw.view(16, 1, 3, 3, 3)
 

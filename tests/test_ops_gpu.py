@@ -175,13 +175,17 @@ def _ndhwc(t):
     return t.permute(0, 2, 3, 4, 1).contiguous()
 
 
-@pytest.mark.parametrize('shape', [(2, 9, 11, 13), (1, 8, 8, 8), (3, 5, 6, 70)])
-def test_conv1_fwd_and_wgrad(dev, shape):
+@pytest.mark.parametrize('impl', ['tc', 'cuda'])
+@pytest.mark.parametrize('shape', [(2, 9, 11, 13), (1, 8, 8, 8), (3, 5, 6, 70), (1, 4, 5, 121), (1, 3, 3, 300)])
+def test_conv1_fwd_and_wgrad(dev, shape, impl, monkeypatch):
     from coinstac_dinunet_b200.ops import vbm
+    monkeypatch.setenv('COINN_CONV1_IMPL', impl)
     torch.manual_seed(1)
     N, D, H, W = shape
     x = torch.randn(N, D, H, W, device=dev)
     w = torch.randn(16, 1, 3, 3, 3, device=dev) * 0.2
+    if impl == 'tc':                       # the tensor-core path rounds x and W to bf16: give the oracle the same
+        x, w = x.bfloat16().float(), w.bfloat16().float()
     y, stats = vbm.conv1_fwd(x, w)
     ref = torch.nn.functional.conv3d(x.unsqueeze(1), w, padding=1)
     assert _rel(y, _ndhwc(ref)) < 5e-3
