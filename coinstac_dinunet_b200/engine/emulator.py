@@ -79,6 +79,7 @@ class InProcessEngine:
         self.round = 0
         self.timings = []
         self.fault_hook = None   # callable(round, site_id) -> raise to inject a failure
+        self._partial = {}       # outputs of sites that already finished the round in flight (retry-safe)
 
     # ------------------------------------------------------------------ shipping
     def _ship_site_to_remote(self, site):
@@ -98,14 +99,20 @@ class InProcessEngine:
     def step(self, local_fn, remote_fn):
         """Run one full round; returns ``success`` reported by the aggregator."""
         t0 = _time.time()
-        site_out = {}
+        # A node call is not idempotent (it consumes a batch / applies an update), so when a round is retried
+        # after a failure the sites that had already completed it are NOT called again: their outputs (and
+        # shipped files) are kept in `_partial` until the round commits.
+        site_out = self._partial
         for site in self.site_ids:
+            if site in site_out:
+                continue
             if self.fault_hook is not None:
                 self.fault_hook(self.round, site)
             res = local_fn(site, self.site_cache[site], self.site_input[site], self.site_state[site])
             site_out[site] = res['output']
             self._ship_site_to_remote(site)
         res = remote_fn(self.remote_cache, site_out, self.remote_state)
+        self._partial = {}
         self._ship_remote_to_sites()
         remote_out = res['output']
         for site in self.site_ids:

@@ -59,7 +59,7 @@ __device__ __forceinline__ void c1_store_row(uint8_t* tile, int p, const float (
 // ------------------------------------------------------------------------------------------------ forward
 constexpr int C1F_THREADS = 192;      // warp 0: idle/setup, warp 1: MMA, warps 2-5: build + epilogue
 
-__global__ void __launch_bounds__(C1F_THREADS, 2)
+__global__ void __launch_bounds__(C1F_THREADS, 4)
 conv1_fwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /*[16][27]*/, __nv_bfloat16* __restrict__ y,
                     float* __restrict__ stats, const C1Dims d) {
     __shared__ __align__(1024) uint8_t a_tile[2][128 * 64];      // K-major, 64 B rows, 64B swizzle
@@ -184,7 +184,7 @@ __device__ __forceinline__ void tma_load_5d_c1(void* smem_dst, const CUtensorMap
         :: "r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
-__global__ void __launch_bounds__(C1W_THREADS, 1)
+__global__ void __launch_bounds__(C1W_THREADS, 3)
 conv1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const float* __restrict__ x, float* __restrict__ dw /*[16][27]*/,
                       const C1Dims d) {
     extern __shared__ uint8_t smem_raw[];
@@ -256,17 +256,26 @@ conv1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const float* 
     } else {
         const int q = warp & 3;
         const int p = q * 32 + lane;
-        float v[27];
+        float v[27], vn[27];
         uint32_t t = 0;
+        int n, dd, h, w0;
+        if (first < d.num_tiles) {
+            c1_tile_coords(d, first, n, dd, h, w0);
+            c1_load_taps(x, d, n, dd, h, w0 + p, w0 + p < d.W, v);               // zero rows beyond the line end
+        }
         for (long long tile = first; tile < d.num_tiles; tile += step, ++t) {
             const uint32_t a = t & 1;
-            int n, dd, h, w0;
-            c1_tile_coords(d, tile, n, dd, h, w0);
-            c1_load_taps(x, d, n, dd, h, w0 + p, w0 + p < d.W, v);               // zero rows beyond the line end
+            const long long nxt = tile + step;
+            if (nxt < d.num_tiles) {                                             // next tile's loads fly during the store
+                c1_tile_coords(d, nxt, n, dd, h, w0);
+                c1_load_taps(x, d, n, dd, h, w0 + p, w0 + p < d.W, vn);
+            }
             mbar_wait(&a_free[a], ((t >> 1) & 1) ^ 1);
             c1_store_row<128>(a ? a_tile1 : a_tile0, p, v);
             fence_proxy_async_smem();
             mbar_arrive(&a_ready[a]);
+#pragma unroll
+            for (int i = 0; i < 27; ++i) v[i] = vn[i];
         }
         if (my_tiles > 0) {
             mbar_wait(done_bar, 0);
@@ -292,7 +301,7 @@ COINN_API int coinn_conv1_fwd_tc(const float* x, const float* w, void* y, float*
     using namespace coinn;
     C1Dims d{N, D, H, W, (W + 127) / 128, 0};
     d.num_tiles = (long long)N * D * H * d.tiles_w;
-    const long long cap = 2LL * B200_SM_COUNT;
+    const long long cap = 4LL * B200_SM_COUNT;      // several small CTAs per SM overlap their per-tile barrier chains
     const int grid = (int)(d.num_tiles < cap ? d.num_tiles : cap);
     conv1_fwd_tc_kernel<<<grid, C1F_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, w, (__nv_bfloat16*)y, stats, d);
     COINN_CHECK_LAUNCH();
@@ -320,7 +329,8 @@ COINN_API int coinn_conv1_wgrad_tc(const void* dy, const float* x, float* dw, in
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    const int grid = (int)(d.num_tiles < B200_SM_COUNT ? d.num_tiles : B200_SM_COUNT);
+    const long long capw = 3LL * B200_SM_COUNT;
+    const int grid = (int)(d.num_tiles < capw ? d.num_tiles : capw);
     conv1_wgrad_tc_kernel<<<grid, C1W_THREADS, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tdy, x, dw, d);
     COINN_CHECK_LAUNCH();
     return 0;

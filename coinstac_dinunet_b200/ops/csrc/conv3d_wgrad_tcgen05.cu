@@ -31,14 +31,13 @@ template <int COUT, int TM> struct WgradCfg {
     static constexpr int A_BYTES = TM * A_TILE;
     static constexpr int B_BYTES = WG_BK * COUT * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    // two stages leave ~90 KB of the 228 KB carve-out to L1, which is what serves the 27x tap re-reads
-    __host__ __device__ static constexpr int stages() { return 2; }
+    __host__ __device__ static constexpr int stages() { return 3; }
     __host__ __device__ static constexpr int smem_bytes() { return stages() * STAGE_BYTES + 1024 + 256; }
 };
 
 __device__ __forceinline__ void cp16z(uint32_t dst, const void* src, bool valid) {
     const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(sz) : "memory");   // .ca: taps overlap -> L1 hits
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(sz) : "memory");
 }
 
 template <int CIN, int COUT, int TM>

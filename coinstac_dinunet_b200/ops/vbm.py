@@ -31,10 +31,18 @@ def _chk(code, what):
 
 
 # ------------------------------------------------------------------------------------ kernels
-def conv1_impl():
-    """'tc' (default): tcgen05 kernels of conv1_tc.cu; 'cuda': the CUDA-core kernels of vbm_fused.cu."""
+def conv1_impl(which='fwd'):
+    """'tc': tcgen05 kernels of conv1_tc.cu; 'cuda': the CUDA-core kernels of vbm_fused.cu.
+    Measured on B200 (profiles/r1_launches_*): forward 611 us (cuda) vs 827 us (tc); wgrad 1180 us (cuda) vs
+    585 us (tc) for the 8 x 121x145x121 batch -> defaults are forward=cuda, wgrad=tc.  COINN_CONV1_IMPL
+    overrides both, COINN_CONV1_FWD / COINN_CONV1_WGRAD one of them."""
     import os
-    return os.environ.get('COINN_CONV1_IMPL', 'tc')
+    both = os.environ.get('COINN_CONV1_IMPL')
+    if both:
+        return both
+    if which == 'fwd':
+        return os.environ.get('COINN_CONV1_FWD', 'cuda')
+    return os.environ.get('COINN_CONV1_WGRAD', 'tc')
 
 
 def conv1_fwd(x, weight, impl=None):
@@ -44,7 +52,7 @@ def conv1_fwd(x, weight, impl=None):
     w = weight.detach().float().reshape(16, 27).contiguous()
     y = _torch.empty((N, D, H, W, 16), dtype=BF16, device=x.device)
     stats = _torch.zeros(32, dtype=_torch.float32, device=x.device)
-    if (impl or conv1_impl()) == 'tc':
+    if (impl or conv1_impl('fwd')) == 'tc':
         _chk(_nat.lib().coinn_conv1_fwd_tc(x.data_ptr(), w.data_ptr(), y.data_ptr(), stats.data_ptr(), N, D, H, W,
                                            _sp(x)), 'coinn_conv1_fwd_tc')
     else:
@@ -58,7 +66,7 @@ def conv1_wgrad(dy, x, impl=None):
     """dy: [N,D,H,W,16] bf16, x: [N,D,H,W] -> dW [16,1,3,3,3] fp32."""
     N, D, H, W = x.shape
     dw = _torch.zeros(16 * 27, dtype=_torch.float32, device=x.device)
-    if (impl or conv1_impl()) == 'tc':
+    if (impl or conv1_impl('wgrad')) == 'tc':
         x = x.float().contiguous()
         _chk(_nat.lib().coinn_conv1_wgrad_tc(dy.contiguous().data_ptr(), x.data_ptr(), dw.data_ptr(), N, D, H, W,
                                              _sp(x)), 'coinn_conv1_wgrad_tc')

@@ -60,6 +60,12 @@ class GraphedStep:
             self.static[k].copy_(v, non_blocking=True)
         self.learner.model.train()
         self.arena.rebind_grads()
+        # the warm-up passes below are real optimizer steps; snapshot everything they mutate and roll back
+        # afterwards so that the first replay is exactly the first training step of the eager schedule
+        ar = self.arena
+        snap = [t.clone() for t in (ar.flat_param, ar.m, ar.v, ar.step_count)]
+        bufs = [(b, b.clone()) for b in self.learner.model.buffers()]
+        counters = (ar.steps_done, ar.host_step)
         side = _torch.cuda.Stream(self.device)
         side.wait_stream(_torch.cuda.current_stream(self.device))
         with _torch.cuda.stream(side):                      # warm-up: lazy inits, cudaFuncSetAttribute, autotune
@@ -83,7 +89,15 @@ class GraphedStep:
         self.it = it
         self.steps_in_ring = 0
         self.cursor.zero_()
-        # the two warm-up steps and the capture pass were real optimizer steps on real data: keep them
+        with _torch.no_grad():
+            for dst, src in zip((ar.flat_param, ar.m, ar.v, ar.step_count), snap):
+                dst.copy_(src)
+            for b, saved in bufs:
+                b.copy_(saved)
+            ar.flat_grad.zero_()
+            if ar.shadow_buf is not None:
+                ar.shadow_buf.local.copy_(ar.flat_param)
+        ar.steps_done, ar.host_step = counters
         return self
 
     # ---------------------------------------------------------------------------------- replay

@@ -83,8 +83,9 @@ class NvlinkLearner(COINNLearner):
         done = 0
         if gs is None or gs.arena is not self.arena:
             batch, _ = self.trainer.data_handle.next_iter()
-            gs = self.cache['_graph_step'] = GraphedStep(self).capture(batch)
-            done = 0                                  # capture consumed one batch but its steps were warm-up
+            gs = self.cache['_graph_step'] = GraphedStep(self).capture(batch)   # state is rolled back after warm-up
+            gs.step(batch)                                                       # ... so this is training step 1
+            done = 1
         for _ in range(steps - done):
             batch, _ = self.trainer.data_handle.next_iter()
             gs.step(batch)

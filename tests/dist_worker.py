@@ -18,9 +18,10 @@ def scenario_protocol(work, opts):
     from coinstac_dinunet_b200.engine import DistEngine
     from coinstac_dinunet_b200.models import FSVDataset, FSVTrainer, write_synthetic_site
     spec = dict(task_id='fsv', mode='train', data_dir='data', labels_file='labels.json', input_size=66, num_class=2,
-                batch_size=4, epochs=2, num_folds=None, split_ratio=[0.6, 0.2, 0.2], learning_rate=1e-2, seed=7,
+                batch_size=4, num_folds=None, split_ratio=[0.6, 0.2, 0.2], learning_rate=1e-2, seed=7,
                 transport=opts.get('transport', 'nvlink'), agg_engine=opts.get('agg_engine', 'dSGD'),
-                start_powerSGD_iter=2, matrix_approximation_rank=2,
+                start_powerSGD_iter=2, matrix_approximation_rank=2, cuda_graph=opts.get('cuda_graph') == '1',
+                epochs=int(opts.get('epochs', 2)),
                 gpus=[int(os.environ.get('LOCAL_RANK', 0))] if torch.cuda.is_available() else None)
     eng = DistEngine(work, inputspec=spec)
     sizes = [24, 18, 30, 12, 20, 16, 28, 22]
@@ -35,6 +36,7 @@ def scenario_protocol(work, opts):
         csv = os.path.join(eng.remote_state['outputDirectory'], 'fsv', 'global_test_metrics.csv')
         res = {'rounds': rounds, 'replicas_identical': bool(same), 'csv': os.path.exists(csv),
                'backend': eng.cache['_arena'].backend, 'fused_steps': eng.cache['_arena'].steps_done,
+               'graphed': '_graph_step' in eng.cache, 'param_sum': float(gathered[0].double().sum()),
                'trace': [t['remote'] for t in eng.trace]}
         with open(os.path.join(work, 'result.json'), 'w') as fp:
             json.dump(res, fp)

@@ -294,3 +294,18 @@ def test_tcgen05_conv3d_wgrad_matches_torch(dev, cin, cout, shape):
         dy.float().permute(0, 4, 1, 2, 3), x.float().permute(0, 4, 1, 2, 3), w, None, [1, 1, 1], [1, 1, 1], [1, 1, 1],
         False, [0, 0, 0], 1, [False, True, False])
     assert _rel(dw, dw_ref) < 5e-3, _rel(dw, dw_ref)
+
+
+def test_cuda_graph_step_matches_eager(tmp_path):
+    """whole-step CUDA graph (forward + loss + metrics + backward + fused optimizer) through the full protocol
+    on one GPU: same trace, same scores file, parameters equal to the eager run up to atomics ordering."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_dist_cpu import run_workers
+    (tmp_path / 'eager').mkdir(); (tmp_path / 'graph').mkdir()
+    eager = run_workers('protocol', tmp_path / 'eager', nproc=1, port=29721, extra=['transport=nvlink'])
+    graph = run_workers('protocol', tmp_path / 'graph', nproc=1, port=29722, extra=['transport=nvlink', 'cuda_graph=1'])
+    assert graph['graphed'] and not eager['graphed']
+    assert graph['trace'] == eager['trace'] and graph['csv']
+    assert graph['fused_steps'] == eager['fused_steps']
+    assert abs(graph['param_sum'] - eager['param_sum']) < 1e-2 * max(1.0, abs(eager['param_sum']))
