@@ -4,6 +4,8 @@ Weight layouts fed to the kernel (bf16, K padded to a multiple of 64 with zeros)
     fprop   Wk[co, tap*Cin + ci]   = W[co, ci, kd, kh, kw]
     dgrad   Wd[ci, tap'*Cout + co] = W[co, ci, 2-kd', 2-kh', 2-kw']      (dx = conv(dy, Wd))
 """
+import os as _os
+
 import torch as _torch
 
 from . import native as _nat
@@ -59,8 +61,10 @@ def _igemm(x, wk, kpad, cout, impl=None):
     lib = _nat.lib()
     args = (x.data_ptr(), wk.data_ptr(), y.data_ptr(), N, D, H, W, cin, cout, kpad, _nat.stream_ptr(x.device))
     code = -1
-    if impl in ('auto', 'halo'):
-        code, last_impl = lib.coinn_conv3d_halo(*args), 'halo'
+    if impl in ('auto', 'halo', 'halo2'):
+        fullpix = 1 if impl == 'halo2' or (impl == 'auto' and _os.environ.get('COINN_HALO_FULLPIX', '0') == '1') else 0
+        code = lib.coinn_conv3d_halo(*args[:-1], fullpix, args[-1])
+        last_impl = 'halo2' if fullpix else 'halo'
     if code == -1 and impl != 'gather':
         code, last_impl = lib.coinn_conv3d_tma(*args), 'tma'
     if code == -1:

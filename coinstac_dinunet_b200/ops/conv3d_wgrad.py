@@ -1,8 +1,11 @@
 """Conv3d weight gradient on the tcgen05 implicit-GEMM kernel (``csrc/conv3d_wgrad_tcgen05.cu``)."""
+import os as _os
+
 import torch as _torch
 
 from . import native as _nat
 
+last_impl = None
 _SUPPORTED = {(16, 32), (32, 64), (64, 128), (128, 256), (32, 32), (64, 64)}
 
 
@@ -13,9 +16,16 @@ def conv3d_wgrad(dy, x):
     if (cin, cout) not in _SUPPORTED:
         raise ImportError(f'no tcgen05 wgrad instantiation for {cin}->{cout}')
     dwt = _torch.zeros((27 * cin, cout), dtype=_torch.float32, device=x.device)
-    code = _nat.lib().coinn_conv3d_wgrad(x.contiguous().data_ptr(), dy.contiguous().data_ptr(), dwt.data_ptr(),
-                                         N, D, H, W, cin, cout, _nat.stream_ptr(x.device))
-    _nat.check(code, f'coinn_conv3d_wgrad({cin}->{cout})')
+    impl = _os.environ.get('COINN_WGRAD_IMPL', 'auto')      # auto: halo kernel where it applies, else the gather kernel
+    args = (x.contiguous().data_ptr(), dy.contiguous().data_ptr(), dwt.data_ptr(), N, D, H, W, cin, cout,
+            _nat.stream_ptr(x.device))
+    global last_impl
+    code = -1
+    if impl in ('auto', 'halo'):
+        code, last_impl = _nat.lib().coinn_conv3d_wgrad_halo(*args), 'halo'
+    if code == -1:
+        code, last_impl = _nat.lib().coinn_conv3d_wgrad(*args), 'gather'
+    _nat.check(code, f'conv3d_wgrad[{last_impl}]({cin}->{cout})')
     from . import _count_launch
     _count_launch()
     # dwt[(kd,kh,kw,ci), co] -> [co, ci, kd, kh, kw]

@@ -33,11 +33,15 @@ __device__ __forceinline__ void tma_load_5d_h(void* smem_dst, const CUtensorMap*
         :: "r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool FULLPIX>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const ConvHaloParams p) {
+    // FULLPIX: one box per d-plane holding whole pixels (CIN*2 = 32/64 bytes, 32B/64B swizzle) - 2-4x fewer and
+    // 2-4x larger TMA requests than the chunk-plane layout (8 channels = 16 B per request, no swizzle).
     constexpr int CHUNKS = CIN / 8;                         // 16-byte channel chunks per pixel
-    constexpr int REGIONS = 3 * CHUNKS;                     // per tile: (d-plane, chunk)
+    constexpr int REGIONS = FULLPIX ? 3 : 3 * CHUNKS;       // per tile: d-planes (x chunk planes)
+    constexpr int PIXB = FULLPIX ? CIN * 2 : 16;            // bytes per pixel inside one region
+    constexpr uint64_t A_LAYOUT = !FULLPIX ? SMEM_LAYOUT_NONE : (CIN == 16 ? SMEM_LAYOUT_SW32 : SMEM_LAYOUT_SW64);
     constexpr int KCH = 27 * CHUNKS;                        // weight k-chunks
     constexpr uint32_t W_CHUNK_BYTES = COUT * 16;
     constexpr uint32_t W_BYTES = (KCH * W_CHUNK_BYTES + 1023) / 1024 * 1024;
@@ -88,10 +92,15 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 uint8_t* dst = stage_base + (size_t)s * stage_bytes;
                 mbar_arrive_expect_tx(&full_bar[s], REGIONS * p.region_tx);
 #pragma unroll
-                for (int kd = 0; kd < 3; ++kd)
+                for (int kd = 0; kd < 3; ++kd) {
+                    if (FULLPIX) {
+                        tma_load_5d_h(dst + kd * p.region_bytes, &tmap_x, &full_bar[s], 0, -1, h0 - 1, d + kd - 1, n);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < CHUNKS; ++c)
-                        tma_load_5d_h(dst + (kd * CHUNKS + c) * p.region_bytes, &tmap_x, &full_bar[s], c * 8, -1, h0 - 1, d + kd - 1, n);
+                        for (int c = 0; c < CHUNKS; ++c)
+                            tma_load_5d_h(dst + (kd * CHUNKS + c) * p.region_bytes, &tmap_x, &full_bar[s], c * 8, -1, h0 - 1, d + kd - 1, n);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -107,20 +116,34 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 mbar_wait(&full_bar[s], (it / STAGES) & 1);
                 tcgen05_after_sync();
                 const uint32_t d_tmem = tmem_base + a * COUT;
-                const uint32_t halo = smem_u32(stage_base + (size_t)s * stage_bytes);
-                uint32_t first = 1;
-#pragma unroll 1
-                for (int tap = 0; tap < 27; ++tap) {
-                    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-                    const uint32_t shift = (uint32_t)(kh * p.Wp + kw) * 16u;
+                // Descriptor = constant part | (address >> 4).  All per-tap offsets are affine in (kd, kh, kw), so the
+                // fully unrolled nest below costs ~3 integer instructions per MMA (the first version divided tap by
+                // 9 and 3 and rebuilt both 64-bit descriptors for every MMA: ~185 cycles of scalar code per MMA in the
+                // single issuing thread, which - not the tensor core - bounded the kernel; see profiles/).
+                const uint32_t halo16 = (smem_u32(stage_base + (size_t)s * stage_bytes) & 0x3FFFFu) >> 4;
+                const uint32_t region16 = p.region_bytes >> 4;
+                const uint32_t row16 = (uint32_t)p.Wp * (PIXB / 16);
+                const uint64_t a_const = FULLPIX ? make_smem_desc(0, 16, 8 * PIXB, A_LAYOUT)
+                                                 : make_smem_desc(0, p.region_bytes, 128, SMEM_LAYOUT_NONE);
+                const uint64_t b_const = make_smem_desc(0, W_CHUNK_BYTES, 128, SMEM_LAYOUT_NONE);
+                uint32_t b16 = (w_addr & 0x3FFFFu) >> 4;
+                uint32_t accumulate = 0;
 #pragma unroll
-                    for (int j = 0; j < CIN / 16; ++j) {
-                        const uint64_t adesc = make_smem_desc(halo + (kd * CHUNKS + 2 * j) * p.region_bytes + shift,
-                                                              p.region_bytes, 128, SMEM_LAYOUT_NONE);
-                        const uint64_t bdesc = make_smem_desc(w_addr + (tap * CHUNKS + 2 * j) * W_CHUNK_BYTES,
-                                                              W_CHUNK_BYTES, 128, SMEM_LAYOUT_NONE);
-                        umma_f16(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
-                        first = 0;
+                for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                            for (int j = 0; j < CIN / 16; ++j) {
+                                const uint32_t a16 = FULLPIX
+                                    ? halo16 + kd * region16 + kh * row16 + kw * (PIXB / 16) + j * 2
+                                    : halo16 + (kd * CHUNKS + 2 * j) * region16 + kh * row16 + kw;
+                                umma_f16(d_tmem, a_const | a16, b_const | b16, idesc, accumulate);
+                                accumulate = 1;
+                                b16 += 2 * (W_CHUNK_BYTES / 16);
+                            }
+                        }
                     }
                 }
                 umma_commit(&empty_bar[s]);
@@ -168,9 +191,10 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool FULLPIX>
 static int launch_conv_halo(const void* x, const void* wk, void* y, int N, int D, int H, int W, int kpad, cudaStream_t st) {
-    constexpr int CHUNKS = CIN / 8, REGIONS = 3 * CHUNKS, KCH = 27 * CHUNKS;
+    constexpr int CHUNKS = CIN / 8, REGIONS = FULLPIX ? 3 : 3 * CHUNKS, KCH = 27 * CHUNKS;
+    constexpr int PIXB = FULLPIX ? CIN * 2 : 16;
     constexpr uint32_t W_BYTES = (KCH * COUT * 16 + 1023) / 1024 * 1024;
     ConvHaloParams p;
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
@@ -182,8 +206,8 @@ static int launch_conv_halo(const void* x, const void* wk, void* y, int N, int D
     if (p.TH + 2 > 256) return -1;
     p.tiles_h = (H + p.TH - 1) / p.TH;
     p.num_tiles = N * D * p.tiles_h;
-    p.region_tx = (uint32_t)(p.TH + 2) * p.Wp * 16u;
-    p.region_bytes = (p.region_tx + 127u) & ~127u;
+    p.region_tx = (uint32_t)(p.TH + 2) * p.Wp * (uint32_t)PIXB;
+    p.region_bytes = (p.region_tx + 1023u) & ~1023u;          // 1 KB: keeps swizzle phases of the regions identical
     const uint32_t stage_bytes = REGIONS * p.region_bytes + 1024;
     const int budget = 220 * 1024 - (int)W_BYTES - 1024 - 512;
     int stages = budget / (int)stage_bytes;
@@ -198,20 +222,21 @@ static int launch_conv_halo(const void* x, const void* wk, void* y, int N, int D
     {
         cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
         cuuint64_t strides[4] = {(cuuint64_t)CIN * 2, (cuuint64_t)W * CIN * 2, (cuuint64_t)H * W * CIN * 2, (cuuint64_t)D * H * W * CIN * 2};
-        cuuint32_t box[5] = {8, (cuuint32_t)p.Wp, (cuuint32_t)(p.TH + 2), 1, 1};
+        cuuint32_t box[5] = {(cuuint32_t)(FULLPIX ? CIN : 8), (cuuint32_t)p.Wp, (cuuint32_t)(p.TH + 2), 1, 1};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         if (enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return -3;
+                FULLPIX ? (CIN == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B) : CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return -3;
     }
     if (make_tmap_2d_bf16(&tw, wk, (uint64_t)COUT, (uint64_t)kpad, (uint64_t)kpad * 2, COUT, 8, CU_TENSOR_MAP_SWIZZLE_NONE) != 0) return -4;
     static int configured = 0;
     if (configured < smem_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(conv3d_halo_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(conv3d_halo_kernel<CIN, COUT, FULLPIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return (int)e;
         configured = smem_bytes;
     }
     const int grid = p.num_tiles < B200_SM_COUNT ? p.num_tiles : B200_SM_COUNT;
-    conv3d_halo_kernel<CIN, COUT><<<grid, CH_THREADS, smem_bytes, st>>>(tx, tw, p);
+    conv3d_halo_kernel<CIN, COUT, FULLPIX><<<grid, CH_THREADS, smem_bytes, st>>>(tx, tw, p);
     COINN_CHECK_LAUNCH();
     return 0;
 }
@@ -219,12 +244,16 @@ static int launch_conv_halo(const void* x, const void* wk, void* y, int N, int D
 }  // namespace coinn
 
 // same contract as coinn_conv3d_igemm; returns -1 when the shape is outside what the halo kernel covers
+// fullpix != 0 selects the whole-pixel (swizzled) halo layout, available for cin in {16, 32}
 COINN_API int coinn_conv3d_halo(const void* x, const void* wk, void* y, int N, int D, int H, int W, int cin, int cout,
-                                int kpad, void* stream) {
+                                int kpad, int fullpix, void* stream) {
     using namespace coinn;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define CASE(CI, CO) if (cin == CI && cout == CO) return launch_conv_halo<CI, CO>(x, wk, y, N, D, H, W, kpad, st);
+#define CASE(CI, CO) if (cin == CI && cout == CO) return launch_conv_halo<CI, CO, false>(x, wk, y, N, D, H, W, kpad, st);
+#define CASEF(CI, CO) if (fullpix && cin == CI && cout == CO) return launch_conv_halo<CI, CO, true>(x, wk, y, N, D, H, W, kpad, st);
+    CASEF(16, 32) CASEF(32, 16) CASEF(32, 64) CASEF(16, 16) CASEF(32, 32)
     CASE(16, 32) CASE(32, 16) CASE(32, 64) CASE(64, 32) CASE(16, 16) CASE(32, 32)
 #undef CASE
+#undef CASEF
     return -1;
 }

@@ -49,7 +49,8 @@ class _Lib:
         d.coinn_conv3d_tma.argtypes = [C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p]
         d.coinn_conv1_fwd_tc.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_conv1_wgrad_tc.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p]
-        d.coinn_conv3d_halo.argtypes = [C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p]
+        d.coinn_conv3d_halo.argtypes = [C.c_void_p] * 3 + [C.c_int] * 8 + [C.c_void_p]
+        d.coinn_conv3d_wgrad_halo.argtypes = [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]
         d.coinn_conv3d_wgrad.argtypes = [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]
         d.coinn_conv1_wgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
 

@@ -260,7 +260,7 @@ def test_native_vbmnet_matches_torch_reference(dev):
                                             (128, 256, (1, 3, 4, 3)), (32, 16, (1, 8, 8, 8)), (256, 128, (2, 3, 4, 3)),
                                             (16, 32, (3, 20, 24, 20)), (16, 32, (1, 5, 7, 60)),
                                             (64, 32, (1, 4, 9, 7))])
-@pytest.mark.parametrize('impl', ['halo', 'tma', 'gather'])
+@pytest.mark.parametrize('impl', ['halo', 'halo2', 'tma', 'gather'])
 def test_tcgen05_conv3d_matches_torch(dev, cin, cout, shape, impl, monkeypatch):
     from coinstac_dinunet_b200.ops.conv3d import conv3d_igemm_fwd, conv3d_igemm_bwd
     monkeypatch.setenv('COINN_CONV_IMPL', impl)
@@ -281,9 +281,12 @@ def test_tcgen05_conv3d_matches_torch(dev, cin, cout, shape, impl, monkeypatch):
 
 
 @pytest.mark.parametrize('cin,cout,shape', [(16, 32, (2, 7, 9, 11)), (32, 64, (1, 6, 5, 9)), (64, 128, (2, 4, 5, 6)),
-                                            (128, 256, (1, 3, 4, 3)), (16, 32, (2, 20, 24, 20))])
-def test_tcgen05_conv3d_wgrad_matches_torch(dev, cin, cout, shape):
+                                            (128, 256, (1, 3, 4, 3)), (16, 32, (2, 20, 24, 20)), (32, 64, (2, 9, 30, 30)),
+                                            (16, 32, (1, 3, 5, 60))])
+@pytest.mark.parametrize('impl', ['halo', 'gather'])
+def test_tcgen05_conv3d_wgrad_matches_torch(dev, cin, cout, shape, impl, monkeypatch):
     from coinstac_dinunet_b200.ops.conv3d_wgrad import conv3d_wgrad
+    monkeypatch.setenv('COINN_WGRAD_IMPL', impl)
     torch.manual_seed(cin * 3 + cout)
     N, D, H, W = shape
     x = torch.randn(N, D, H, W, cin, device=dev).to(torch.bfloat16)
