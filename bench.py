@@ -37,8 +37,8 @@ FS_SHAPE = (66,)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--model', default='vbm', choices=['vbm', 'fs'])
     ap.add_argument('--batch', type=int, default=None, help='per-site batch (default 8 vbm / 16 fs)')
@@ -47,12 +47,13 @@ def parse():
     ap.add_argument('--variant', default='auto', choices=['auto', 'one_shot', 'two_shot', 'nvls'])
     ap.add_argument('--native', type=int, default=1, help='use the hand-written sm_100a model kernels')
     ap.add_argument('--skip-e2e', action='store_true')
+    ap.add_argument('--graph', type=int, default=1, help='capture the whole step in a CUDA graph')
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """`nvidia-smi` clocks + throttle reasons sampled every 200 ms during the timed region."""
+    """`nvidia-smi` clocks + throttle reasons sampled every 25 ms during the timed region."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
@@ -65,7 +66,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.index), '-lms', '200'],
+                                          '-i', str(self.index), '-lms', '25'],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -163,7 +164,7 @@ def run_ours(a):
                 monitor_metric='f1', learning_rate=1e-3, validation_epochs=10 ** 9, transport=a.transport, reduce_variant=a.variant,
                 compute_dtype=a.dtype, channels_last='3d' if a.model == 'vbm' else None, native_ops=bool(a.native),
                 input_shape=list(shape), input_size=shape[0], synthetic_distinct=n_distinct,
-                reference_order=True, pin_memory=False, collate_fn=pinned_collate)
+                reference_order=True, pin_memory=False, collate_fn=pinned_collate, cuda_graph=bool(a.graph))
     eng = DistEngine(work, inputspec=spec)
     data_dir = os.path.join(eng.state['baseDirectory'], 'data')
     os.makedirs(data_dir, exist_ok=True)
@@ -190,6 +191,8 @@ def run_ours(a):
         eng.cache['steps_per_round'] = k
         eng.cache['readback_per_step'] = readback
         eng.cache['synthetic_device'] = f'cuda:{local}' if resident else None
+        # end-to-end mode: stage batch t+1 on a copy stream while step t computes (public dataloader option)
+        eng.cache['prefetch_to_device'] = None if resident else f'cuda:{local}'
         ds = eng.cache['dataset'].get('train')
         if ds is not None and (ds._x is None or (ds._x.is_cuda != resident)):
             ds._x = None                                     # re-materialise on the requested side
@@ -232,7 +235,7 @@ def run_ours(a):
                        'input': list(shape), 'per_site_batch': batch, 'global_batch': batch * a.gpus,
                        'parallelism': f'dSGD sites={a.gpus} (1 site/GPU)', 'optimizer': 'Adam(1e-3)',
                        'transport': arena.backend, 'reduce_variant': arena._pick_variant(arena.numel * 4),
-                       'native_model_kernels': bool(a.native),
+                       'native_model_kernels': bool(a.native), 'cuda_graph': bool(a.graph),
                        'l2_policy': 'inputs rotate over 4 distinct batches; activations per step >> 126 MB L2'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
         }

@@ -15,8 +15,12 @@ FS_HIDDEN = (256, 128, 64, 32)
 
 
 class FSNet(_nn.Module):
-    def __init__(self, in_size=FS_INPUT_SIZE, hidden_sizes=FS_HIDDEN, out_size=2):
+    """``native=True``: the Linear layers (forward, dgrad, wgrad) run on the tcgen05 GEMM of
+    ``ops/csrc/gemm_tcgen05.cu`` with the bias fused into the epilogue; parameters / state_dict are unchanged."""
+
+    def __init__(self, in_size=FS_INPUT_SIZE, hidden_sizes=FS_HIDDEN, out_size=2, native=False):
         super().__init__()
+        self.native = bool(native)
         dims = [in_size, *hidden_sizes]
         blocks = []
         for a, b in zip(dims[:-1], dims[1:]):
@@ -24,8 +28,22 @@ class FSNet(_nn.Module):
         self.features = _nn.Sequential(*blocks)
         self.classifier = _nn.Linear(dims[-1], out_size)
 
+    @property
+    def is_native(self):
+        return self.native
+
     def forward(self, x):
-        return self.classifier(self.features(x.reshape(x.shape[0], -1)))
+        x = x.reshape(x.shape[0], -1)
+        if self.native and x.is_cuda:
+            from ..ops.linear import LinearFn
+            h = x
+            for layer in self.features:
+                if isinstance(layer, _nn.Linear):
+                    h = LinearFn.apply(h, layer.weight, layer.bias, False).float()
+                else:
+                    h = layer(h)
+            return LinearFn.apply(h, self.classifier.weight, self.classifier.bias, False).float()
+        return self.classifier(self.features(x))
 
 
 class FSVDataset(ArrayFileDataset):
@@ -36,4 +54,5 @@ class FSVTrainer(ClassificationTrainer):
     def _init_nn_model(self):
         self.nn['fs_net'] = FSNet(in_size=self.cache.get('input_size', FS_INPUT_SIZE),
                                   hidden_sizes=tuple(self.cache.get('hidden_sizes', FS_HIDDEN)),
-                                  out_size=self.cache.get('num_class', 2))
+                                  out_size=self.cache.get('num_class', 2),
+                                  native=bool(self.cache.get('native_ops', False)))

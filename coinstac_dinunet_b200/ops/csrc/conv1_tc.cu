@@ -24,19 +24,27 @@ __device__ __forceinline__ void c1_tile_coords(const C1Dims& d, long long tile, 
     n = (int)(tile / d.D);
 }
 
-// 27 neighbourhood values of pixel (n, dd, h, w) (zero outside the volume); loads are independent -> all in flight
+// 27 neighbourhood values of pixel (n, dd, h, w) (zero outside the volume).  One 32-bit centre offset + constant tap
+// offsets and three 3-bit validity masks: no per-tap multiplies, all 27 loads independent (in flight together).
 __device__ __forceinline__ void c1_load_taps(const float* __restrict__ x, const C1Dims& d, int n, int dd, int h, int w, bool active,
                                              float (&v)[27]) {
+    const int HW = d.H * d.W;
+    const int centre = ((n * d.D + dd) * d.H + h) * d.W + w;           // < 2^31 elements for any volume we support
+    const uint32_t vd = active ? ((dd > 0 ? 1u : 0u) | 2u | (dd + 1 < d.D ? 4u : 0u)) : 0u;
+    const uint32_t vh = (h > 0 ? 1u : 0u) | 2u | (h + 1 < d.H ? 4u : 0u);
+    const uint32_t vw = (w > 0 ? 1u : 0u) | 2u | (w + 1 < d.W ? 4u : 0u);
+    const float* c = x + centre;
 #pragma unroll
-    for (int r = 0; r < 9; ++r) {
-        const int zd = dd + r / 3 - 1, zh = h + r % 3 - 1;
-        const bool row_ok = active && zd >= 0 && zd < d.D && zh >= 0 && zh < d.H;
-        const float* row = x + (((long long)n * d.D + (row_ok ? zd : 0)) * d.H + (row_ok ? zh : 0)) * d.W;
+    for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-            const int zw = w + kw - 1;
-            const bool ok = row_ok && zw >= 0 && zw < d.W;
-            v[r * 3 + kw] = ok ? __ldg(row + zw) : 0.f;
+        for (int kh = 0; kh < 3; ++kh) {
+            const bool row_ok = ((vd >> kd) & 1u) && ((vh >> kh) & 1u);
+            const int roff = (kd - 1) * HW + (kh - 1) * d.W;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const bool ok = row_ok && ((vw >> kw) & 1u);
+                v[(kd * 3 + kh) * 3 + kw] = ok ? __ldg(c + roff + (kw - 1)) : 0.f;
+            }
         }
     }
 }

@@ -344,6 +344,52 @@ __global__ void __launch_bounds__(256, APPLY ? 1 : 2) bn_relu_pool_bwd_kernel(co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pass A without touching y:  the pooled output already carries what the reductions need.
+//   z_argmax = relu-input at the arg-max = p (when p > 0)   =>   xhat_argmax = (p - beta) / gamma
+//   dbeta[c]  = sum_cells dp * [p > 0]          dgamma[c] = sum_cells dp * [p > 0] * (p - beta) / gamma
+// p, dp: [cells, C] bf16 (1/8 of y).  acc[0:C] += dbeta, acc[C:2C] += dgamma.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_pool_bwd_stats_pooled_kernel(const __nv_bfloat16* __restrict__ p, const __nv_bfloat16* __restrict__ dp,
+                                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                       float* __restrict__ acc, long long cells, int C) {
+    extern __shared__ float sm[];
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int chunks = C >> 3;
+    const int my_chunk = threadIdx.x % chunks;
+    const int rows_per_iter = blockDim.x / chunks;
+    const int my_row = threadIdx.x / chunks;
+    float be[8], ig[8], a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float g = gamma[my_chunk * 8 + j];
+        be[j] = beta[my_chunk * 8 + j];
+        ig[j] = fabsf(g) > 1e-12f ? 1.f / g : 0.f;
+        a0[j] = 0.f; a1[j] = 0.f;
+    }
+    if (my_row < rows_per_iter) {
+        for (long long m = (long long)blockIdx.x * rows_per_iter + my_row; m < cells; m += (long long)gridDim.x * rows_per_iter) {
+            float pv[8], gv[8];
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4*>(p + m * C) + my_chunk), pv);
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4*>(dp + m * C) + my_chunk), gv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float g = pv[j] > 0.f ? gv[j] : 0.f;
+                a0[j] += g;
+                a1[j] = fmaf(g, (pv[j] - be[j]) * ig[j], a1[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sm[my_chunk * 8 + j], a0[j]);
+            atomicAdd(&sm[C + my_chunk * 8 + j], a1[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&acc[i], sm[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // conv1 wgrad: dW[co, tap] += sum_vox dy[vox, co] * x[vox + tap]      (dy: [N,D,H,W,16] bf16, x: [N,D,H,W])
 // lane = tap (27 of 32 lanes active), 16 output channels in registers, dy row broadcast from shared memory.
 // ------------------------------------------------------------------------------------------------
@@ -493,6 +539,21 @@ COINN_API int coinn_bn_relu_pool_bwd(const void* y, const void* dp, const float*
                                                                    gamma, beta, acc, (__nv_bfloat16*)dy, d, C, inv_count);
     else bn_relu_pool_bwd_kernel<false><<<grid, 256, 2 * C * sizeof(float), st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)dp, mean,
                                                                                    invstd, gamma, beta, acc, nullptr, d, C, inv_count);
+    COINN_CHECK_LAUNCH();
+    return 0;
+}
+
+// acc[2C] (zeroed) += (dbeta, dgamma) computed from the pooled output p and its gradient dp only
+COINN_API int coinn_bn_pool_bwd_stats_pooled(const void* p, const void* dp, const float* gamma, const float* beta, float* acc,
+                                             long long cells, int C, void* stream) {
+    using namespace coinn;
+    if (C % 8 || C > 256 || 256 % (C / 8)) return (int)cudaErrorInvalidValue;
+    if (cells == 0) return 0;
+    const int rows_per_iter = 256 / (C / 8);
+    long long want = (cells + (long long)rows_per_iter * 8 - 1) / ((long long)rows_per_iter * 8);
+    const int grid = (int)(want < 1 ? 1 : (want > 4LL * B200_SM_COUNT ? 4LL * B200_SM_COUNT : want));
+    bn_pool_bwd_stats_pooled_kernel<<<grid, 256, 2 * C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, gamma, beta, acc, cells, C);
     COINN_CHECK_LAUNCH();
     return 0;
 }

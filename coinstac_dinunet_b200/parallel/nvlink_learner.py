@@ -28,6 +28,43 @@ def _dist_on():
     return _dist.is_available() and _dist.is_initialized()
 
 
+class _LaggedReadback:
+    """Per-step device->host read of the loss without stalling the launch pipeline: step t's loss is copied
+    asynchronously into a pinned slot and *consumed* (event-synchronised) while step t+1 is already queued."""
+
+    def __init__(self, device, slots=4):
+        self.buf = _torch.zeros(slots, dtype=_torch.float32).pin_memory() if device.type == 'cuda' else _torch.zeros(slots)
+        self.events = [None] * slots
+        self.slots, self.count, self.head, self.last = slots, 0, 0, float('nan')
+        self.cuda = device.type == 'cuda'
+
+    def _consume(self, i):
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+            self.last = float(self.buf[i])
+            self.events[i] = None
+            self.count += 1
+
+    def push(self, loss):
+        i = self.head % self.slots
+        self._consume(i)                                   # slot reuse => at most `slots-1` steps of lag
+        self.buf[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        if self.cuda:
+            ev = _torch.cuda.Event()
+            ev.record()
+            self.events[i] = ev
+        else:
+            self.last, self.count = float(self.buf[i]), self.count + 1
+        if self.head >= 1:
+            self._consume((self.head - 1) % self.slots)    # read step t-1 now that step t is queued
+        self.head += 1
+
+    def finish(self):
+        for i in range(self.slots):
+            self._consume((self.head + i) % self.slots)
+        return self.last
+
+
 class NvlinkLearner(COINNLearner):
     @property
     def arena(self):
@@ -86,11 +123,17 @@ class NvlinkLearner(COINNLearner):
             gs = self.cache['_graph_step'] = GraphedStep(self).capture(batch)   # state is rolled back after warm-up
             gs.step(batch)                                                       # ... so this is training step 1
             done = 1
+        rb = _LaggedReadback(self.device) if self.cache.get('readback_per_step') else None
+        if rb is not None and done:
+            rb.push(gs.it['loss'])
         for _ in range(steps - done):
             batch, _ = self.trainer.data_handle.next_iter()
             gs.step(batch)
-            if self.cache.get('readback_per_step'):
-                self.cache['last_loss'] = float(gs.it['loss'].detach())
+            if rb is not None:
+                rb.push(gs.it['loss'])
+        if rb is not None:
+            self.cache['last_loss'] = rb.finish()
+            self.cache['losses_read'] = rb.count
         avg, met = gs.drain()
         return {'averages': avg, 'metrics': met}
 
@@ -104,12 +147,16 @@ class NvlinkLearner(COINNLearner):
             out['mode'] = Mode.VALIDATION_WAITING
             out['fused_steps'] = self.arena.steps_done
             return it, out
+        rb = _LaggedReadback(self.device) if self.cache.get('readback_per_step') else None
         for _ in range(self._steps_this_round()):
             step_its, flags = self.backward()
             self.arena.reduce_and_step()
-            if self.cache.get('readback_per_step'):      # end-to-end mode: the caller wants the loss now
-                self.cache['last_loss'] = float(step_its[-1]['loss'].detach())
+            if rb is not None:                            # end-to-end mode: every step's loss goes to the host
+                rb.push(step_its[-1]['loss'])
             its.extend(step_its)
+        if rb is not None:
+            self.cache['last_loss'] = rb.finish()
+            self.cache['losses_read'] = rb.count
         # the round IS the epoch: report it finished regardless of where the local cursor is
         self.cache['cursor'] = 0
         out['mode'] = Mode.VALIDATION_WAITING

@@ -230,6 +230,10 @@ def test_bn_relu_pool_block_matches_torch(dev, C, shape):
     dy, dgamma, dbeta = vbm.bn_relu_pool_bwd(y, _ndhwc(dp).to(torch.bfloat16), mean, invstd, gamma, beta)
     assert _rel(dgamma, bn.weight.grad) < 2e-2 and _rel(dbeta, bn.bias.grad) < 2e-2
     assert _rel(dy, _ndhwc(y_ref.grad)) < 2e-2
+    # pass A from the pooled tensors only (xhat_argmax = (p - beta) / gamma)
+    dy2, dgamma2, dbeta2 = vbm.bn_relu_pool_bwd(y, _ndhwc(dp).to(torch.bfloat16), mean, invstd, gamma, beta, p=p)
+    assert _rel(dgamma2, bn.weight.grad) < 3e-2 and _rel(dbeta2, bn.bias.grad) < 2e-2
+    assert _rel(dy2, _ndhwc(y_ref.grad)) < 2.5e-2
 
 
 def test_native_vbmnet_matches_torch_reference(dev):
@@ -301,7 +305,9 @@ def test_tcgen05_conv3d_wgrad_matches_torch(dev, cin, cout, shape, impl, monkeyp
 
 def test_cuda_graph_step_matches_eager(tmp_path):
     """whole-step CUDA graph (forward + loss + metrics + backward + fused optimizer) through the full protocol
-    on one GPU: same trace, same scores file, parameters equal to the eager run up to atomics ordering."""
+    on one GPU: same round trace, same number of fused steps, scores written.  (Final parameters are those of the
+    *selected* checkpoint; on 20-sample folds model selection can flip on a 1e-7 loss difference, so exact parameter
+    equality is asserted by test_cuda_graph_replay_bit_equals_eager below instead.)"""
     import os, sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from test_dist_cpu import run_workers
@@ -311,4 +317,46 @@ def test_cuda_graph_step_matches_eager(tmp_path):
     assert graph['graphed'] and not eager['graphed']
     assert graph['trace'] == eager['trace'] and graph['csv']
     assert graph['fused_steps'] == eager['fused_steps']
-    assert abs(graph['param_sum'] - eager['param_sum']) < 1e-2 * max(1.0, abs(eager['param_sum']))
+
+
+def test_cuda_graph_replay_bit_equals_eager(dev):
+    """GraphedStep (capture with rollback, replay, ring-buffer drain) vs the eager NvlinkLearner loop."""
+    from coinstac_dinunet_b200.models import FSNet
+    from coinstac_dinunet_b200.models.common import ClassificationTrainer
+    from coinstac_dinunet_b200.parallel.arena import DistArena
+    from coinstac_dinunet_b200.parallel.graph_step import GraphedStep
+    from coinstac_dinunet_b200.distrib.nodes.remote import EmptyDataHandle
+
+    class T(ClassificationTrainer):
+        def _init_nn_model(self):
+            self.nn['fs_net'] = FSNet()
+
+    def make():
+        cache = {'mode': 'train', 'seed': 3, 'learning_rate': 1e-2, 'num_class': 2, 'monitor_metric': 'f1', 'gpus': [0]}
+        tr = T(data_handle=EmptyDataHandle(cache, {}, {}))
+        tr.init_nn(init_model=True, init_optim=True, set_devices=True, init_weights=True)
+        model, opt = tr.nn['fs_net'], tr.optimizer['adam']
+        arena = DistArena(model, opt, device=dev, backend='nvlink')
+        learner = type('L', (), {})()
+        learner.trainer, learner.arena, learner.device, learner.model = tr, arena, dev, model
+        return tr, arena, learner
+
+    g = torch.Generator().manual_seed(1)
+    batches = [{'inputs': torch.randn(8, 66, generator=g), 'labels': torch.randint(0, 2, (8,), generator=g)} for _ in range(6)]
+    tr1, a1, _ = make()
+    tr1.nn['fs_net'].train()
+    losses, tp = [], 0
+    for b in batches:
+        it = tr1.iteration(b)
+        it['loss'].backward()
+        a1.reduce_and_step()
+        losses.append(float(it['loss'].detach())); tp += it['metrics'].tp + it['metrics'].tn
+    tr2, a2, learner = make()
+    gs = GraphedStep(learner).capture(batches[0])
+    for b in batches:
+        gs.step(b)
+    avg, met = gs.drain()
+    assert torch.equal(a1.flat_param, a2.flat_param)
+    assert abs(float(avg.get()[0]) - sum(losses) / len(losses)) < 1e-4
+    assert met.tp + met.tn == tp and met.tp + met.tn + met.fp + met.fn == 48
+    assert int(a2.step_count) == 6 and gs.kernels_per_replay >= 3
