@@ -53,6 +53,32 @@ def conv_impl():
 last_impl = None
 
 
+_pack_buffers = {}
+_pack_stamp = {}      # which tensor object / version the cached pack belongs to
+
+
+def pack_weights(weight):
+    """Both GEMM operand layouts of a conv weight in ONE launch (``vbm_fused.cu::pack_conv_weights_kernel``).
+    The bf16 buffers persist per parameter (their zero padding is written once); contents are refreshed on every
+    call because the optimizer changes the weights every step.  Returns (wf, kf, wd, kd)."""
+    cout, cin = weight.shape[:2]
+    kf, kd = (27 * cin + 63) // 64 * 64, (27 * cout + 63) // 64 * 64
+    key = (weight.data_ptr(), cout, cin, weight.device)
+    bufs = _pack_buffers.get(key)
+    if bufs is None:
+        bufs = (_torch.zeros((cout, kf), dtype=BF16, device=weight.device),
+                _torch.zeros((cin, kd), dtype=BF16, device=weight.device))
+        _pack_buffers[key] = bufs
+    w32 = weight.detach()
+    if w32.dtype != _torch.float32 or not w32.is_contiguous():
+        w32 = w32.float().contiguous()
+    _nat.check(_nat.lib().coinn_pack_conv_weights(w32.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), cout, cin, kf, kd,
+                                                  _nat.stream_ptr(weight.device)), 'coinn_pack_conv_weights')
+    _bump()
+    _pack_stamp[key] = (id(weight), weight._version)
+    return bufs[0], kf, bufs[1], kd
+
+
 def _igemm(x, wk, kpad, cout, impl=None):
     global last_impl
     N, D, H, W, cin = x.shape
@@ -79,7 +105,7 @@ def conv3d_igemm_fwd(x, weight):
     cout, cin = weight.shape[:2]
     if not supported(cin, cout):
         raise ImportError(f'no tcgen05 conv instantiation for {cin}->{cout}')
-    wk, kpad = pack_fprop_weight(weight)
+    wk, kpad, _, _ = pack_weights(weight)
     return _igemm(x.contiguous(), wk, kpad, cout)
 
 
@@ -89,7 +115,11 @@ def conv3d_igemm_bwd(dy, x, weight, need_dx=True):
         raise ImportError(f'no tcgen05 conv instantiation for dgrad {cout}->{cin}')
     dx = None
     if need_dx:
-        wd, kpad = pack_dgrad_weight(weight)
+        key = (weight.data_ptr(), cout, cin, weight.device)
+        if _pack_stamp.get(key) == (id(weight), weight._version):   # packed by this step's forward, weights unchanged since
+            wd, kpad = _pack_buffers[key][1], (27 * cout + 63) // 64 * 64
+        else:
+            _, _, wd, kpad = pack_weights(weight)
         dx = _igemm(dy.contiguous(), wd, kpad, cin)
     try:
         from .conv3d_wgrad import conv3d_wgrad

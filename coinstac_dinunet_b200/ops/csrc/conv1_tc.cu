@@ -17,23 +17,28 @@ namespace coinn {
 
 struct C1Dims { int N, D, H, W; int tiles_w; long long num_tiles; };
 
-__device__ __forceinline__ void c1_tile_coords(const C1Dims& d, long long tile, int& n, int& dd, int& h, int& w0) {
-    w0 = (int)(tile % d.tiles_w) * 128; tile /= d.tiles_w;
-    h = (int)(tile % d.H); tile /= d.H;
-    dd = (int)(tile % d.D);
-    n = (int)(tile / d.D);
+__device__ __forceinline__ void c1_tile_coords(const C1Dims& d, long long tile64, int& n, int& dd, int& h, int& w0) {
+    unsigned tile = (unsigned)tile64;                      // < 2^31 tiles: 32-bit divisions are ~3x cheaper
+    if (d.tiles_w == 1) { w0 = 0; } else { w0 = (int)(tile % (unsigned)d.tiles_w) * 128; tile /= (unsigned)d.tiles_w; }
+    h = (int)(tile % (unsigned)d.H); tile /= (unsigned)d.H;
+    dd = (int)(tile % (unsigned)d.D);
+    n = (int)(tile / (unsigned)d.D);
 }
 
 // 27 neighbourhood values of pixel (n, dd, h, w) (zero outside the volume).  One 32-bit centre offset + constant tap
 // offsets and three 3-bit validity masks: no per-tap multiplies, all 27 loads independent (in flight together).
-__device__ __forceinline__ void c1_load_taps(const float* __restrict__ x, const C1Dims& d, int n, int dd, int h, int w, bool active,
+__device__ __forceinline__ float c1_ld(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float c1_ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename TX>
+__device__ __forceinline__ void c1_load_taps(const TX* __restrict__ x, const C1Dims& d, int n, int dd, int h, int w, bool active,
                                              float (&v)[27]) {
     const int HW = d.H * d.W;
     const int centre = ((n * d.D + dd) * d.H + h) * d.W + w;           // < 2^31 elements for any volume we support
     const uint32_t vd = active ? ((dd > 0 ? 1u : 0u) | 2u | (dd + 1 < d.D ? 4u : 0u)) : 0u;
     const uint32_t vh = (h > 0 ? 1u : 0u) | 2u | (h + 1 < d.H ? 4u : 0u);
     const uint32_t vw = (w > 0 ? 1u : 0u) | 2u | (w + 1 < d.W ? 4u : 0u);
-    const float* c = x + centre;
+    const TX* c = x + centre;
 #pragma unroll
     for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
@@ -43,7 +48,7 @@ __device__ __forceinline__ void c1_load_taps(const float* __restrict__ x, const 
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
                 const bool ok = row_ok && ((vw >> kw) & 1u);
-                v[(kd * 3 + kh) * 3 + kw] = ok ? __ldg(c + roff + (kw - 1)) : 0.f;
+                v[(kd * 3 + kh) * 3 + kw] = ok ? c1_ld(c + roff + (kw - 1)) : 0.f;
             }
         }
     }
@@ -67,8 +72,9 @@ __device__ __forceinline__ void c1_store_row(uint8_t* tile, int p, const float (
 // ------------------------------------------------------------------------------------------------ forward
 constexpr int C1F_THREADS = 192;      // warp 0: idle/setup, warp 1: MMA, warps 2-5: build + epilogue
 
+template <typename TX>
 __global__ void __launch_bounds__(C1F_THREADS, 4)
-conv1_fwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /*[16][27]*/, __nv_bfloat16* __restrict__ y,
+conv1_fwd_tc_kernel(const TX* __restrict__ x, const float* __restrict__ w /*[16][27]*/, __nv_bfloat16* __restrict__ y,
                     float* __restrict__ stats, const C1Dims d) {
     __shared__ __align__(1024) uint8_t a_tile[2][128 * 64];      // K-major, 64 B rows, 64B swizzle
     __shared__ __align__(1024) uint8_t b_tile[16 * 64];          // W1 [16 co x 32 taps], same layout
@@ -139,8 +145,7 @@ conv1_fwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /*[
                 c1_tile_coords(d, nxt, n2, d2, h2, w2);
                 c1_load_taps(x, d, n2, d2, h2, w2 + p, w2 + p < d.W, v);
             }
-            // ---- epilogue of tile t
-            c1_tile_coords(d, tile, n, dd, h, w0);
+            // ---- epilogue of tile t (its coordinates were decoded one iteration ago)
             mbar_wait(&tmem_full[a], (t >> 1) & 1);
             tcgen05_after_sync();
             uint32_t r[16];
@@ -168,6 +173,7 @@ conv1_fwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /*[
                 c1_store_row<64>(a_tile[a ^ 1], p, v);
                 fence_proxy_async_smem();
                 mbar_arrive(&a_ready[a ^ 1]);
+                n = n2; dd = d2; h = h2; w0 = w2;
             }
         }
 #pragma unroll
@@ -192,8 +198,9 @@ __device__ __forceinline__ void tma_load_5d_c1(void* smem_dst, const CUtensorMap
         :: "r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
+template <typename TX>
 __global__ void __launch_bounds__(C1W_THREADS, 3)
-conv1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const float* __restrict__ x, float* __restrict__ dw /*[16][27]*/,
+conv1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const TX* __restrict__ x, float* __restrict__ dw /*[16][27]*/,
                       const C1Dims d) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -304,20 +311,22 @@ conv1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const float* 
 
 }  // namespace coinn
 
-// x: [N,D,H,W] fp32; w: [16,27] fp32; y: [N,D,H,W,16] bf16; stats: 32 floats (zeroed)
-COINN_API int coinn_conv1_fwd_tc(const float* x, const float* w, void* y, float* stats, int N, int D, int H, int W, void* stream) {
+// x: [N,D,H,W] fp32 (x_dtype 0) or bf16 (1); w: [16,27] fp32; y: [N,D,H,W,16] bf16; stats: 32 floats (zeroed)
+COINN_API int coinn_conv1_fwd_tc(const void* x, int x_dtype, const float* w, void* y, float* stats, int N, int D, int H, int W, void* stream) {
     using namespace coinn;
     C1Dims d{N, D, H, W, (W + 127) / 128, 0};
     d.num_tiles = (long long)N * D * H * d.tiles_w;
     const long long cap = 4LL * B200_SM_COUNT;      // several small CTAs per SM overlap their per-tile barrier chains
     const int grid = (int)(d.num_tiles < cap ? d.num_tiles : cap);
-    conv1_fwd_tc_kernel<<<grid, C1F_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, w, (__nv_bfloat16*)y, stats, d);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (x_dtype == 0) conv1_fwd_tc_kernel<float><<<grid, C1F_THREADS, 0, st>>>((const float*)x, w, (__nv_bfloat16*)y, stats, d);
+    else conv1_fwd_tc_kernel<__nv_bfloat16><<<grid, C1F_THREADS, 0, st>>>((const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, stats, d);
     COINN_CHECK_LAUNCH();
     return 0;
 }
 
-// dy: [N,D,H,W,16] bf16; x: [N,D,H,W] fp32; dw: [16*27] fp32 (zeroed)
-COINN_API int coinn_conv1_wgrad_tc(const void* dy, const float* x, float* dw, int N, int D, int H, int W, void* stream) {
+// dy: [N,D,H,W,16] bf16; x: [N,D,H,W] fp32 (x_dtype 0) or bf16 (1); dw: [16*27] fp32 (zeroed)
+COINN_API int coinn_conv1_wgrad_tc(const void* dy, const void* x, int x_dtype, float* dw, int N, int D, int H, int W, void* stream) {
     using namespace coinn;
     C1Dims d{N, D, H, W, (W + 127) / 128, 0};
     d.num_tiles = (long long)N * D * H * d.tiles_w;
@@ -333,13 +342,16 @@ COINN_API int coinn_conv1_wgrad_tc(const void* dy, const float* x, float* dw, in
     const int smem_bytes = 49152 + C1W_STAGES * 4096 + 256 + 1024;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv1_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(conv1_wgrad_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv1_wgrad_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     const long long capw = 3LL * B200_SM_COUNT;
     const int grid = (int)(d.num_tiles < capw ? d.num_tiles : capw);
-    conv1_wgrad_tc_kernel<<<grid, C1W_THREADS, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tdy, x, dw, d);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (x_dtype == 0) conv1_wgrad_tc_kernel<float><<<grid, C1W_THREADS, smem_bytes, st>>>(tdy, (const float*)x, dw, d);
+    else conv1_wgrad_tc_kernel<__nv_bfloat16><<<grid, C1W_THREADS, smem_bytes, st>>>(tdy, (const __nv_bfloat16*)x, dw, d);
     COINN_CHECK_LAUNCH();
     return 0;
 }

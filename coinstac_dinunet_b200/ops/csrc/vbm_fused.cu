@@ -344,6 +344,92 @@ __global__ void __launch_bounds__(256, APPLY ? 1 : 2) bn_relu_pool_bwd_kernel(co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pass B, 4 channels (8 bytes) per thread: half the per-thread state of the 8-channel version (<= 96 registers,
+// 2-3 CTAs per SM instead of 1), which is what a latency-bound streaming kernel needs to approach the copy roofline.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack4(const uint2& u, float (&f)[4]) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+}
+__global__ void __launch_bounds__(256, 2) bn_relu_pool_bwd_apply4_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dp,
+                                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                        const float* __restrict__ acc, __nv_bfloat16* __restrict__ dy,
+                                                                        Dims d, int C, float inv_count) {
+    const int chunks = C >> 2;                            // 8-byte chunks per voxel
+    const int PD = d.D >> 1, PH = d.H >> 1, PW = d.W >> 1;
+    const int CD = (d.D + 1) >> 1, CH = (d.H + 1) >> 1, CW = (d.W + 1) >> 1;
+    const int my_chunk = threadIdx.x % chunks;
+    const int cells_per_iter = blockDim.x / chunks;
+    const int my_cell_off = threadIdx.x / chunks;
+    const long long total_cells = (long long)d.N * CD * CH * CW;
+    if (my_cell_off >= cells_per_iter) return;
+
+    float sc[4], sh[4], mu[4], is[4], c1[4], c2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = my_chunk * 4 + j;
+        mu[j] = mean[c]; is[j] = invstd[c];
+        sc[j] = gamma[c] * is[j];
+        sh[j] = beta[c] - mu[j] * sc[j];
+        c1[j] = acc[c] * inv_count;
+        c2[j] = acc[C + c] * inv_count;
+    }
+    for (long long cell = (long long)blockIdx.x * cells_per_iter + my_cell_off; cell < total_cells;
+         cell += (long long)gridDim.x * cells_per_iter) {
+        long long t = cell;
+        const int pw = (int)(t % CW); t /= CW;
+        const int ph = (int)(t % CH); t /= CH;
+        const int pd = (int)(t % CD);
+        const int n = (int)(t / CD);
+        const bool pooled = pd < PD && ph < PH && pw < PW;
+        uint2 raw[8];
+        uint2 graw = make_uint2(0u, 0u);
+        if (pooled) {
+            const long long pv = (((long long)n * PD + pd) * PH + ph) * PW + pw;
+            graw = ld_stream_u2(reinterpret_cast<const uint2*>(dp + pv * C) + my_chunk);
+        }
+        long long vox[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int zd = 2 * pd + (k >> 2), zh = 2 * ph + ((k >> 1) & 1), zw = 2 * pw + (k & 1);
+            const bool in = zd < d.D && zh < d.H && zw < d.W;
+            vox[k] = in ? (((long long)n * d.D + zd) * d.H + zh) * d.W + zw : -1;
+            raw[k] = in ? ld_stream_u2(reinterpret_cast<const uint2*>(y + vox[k] * C) + my_chunk) : make_uint2(0u, 0u);
+        }
+        float g[4], best[4];
+        int arg[4];
+        unpack4(graw, g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float f[4];
+            unpack4(raw[k], f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float z = fmaf(f[j], sc[j], sh[j]);
+                if (z > best[j]) { best[j] = z; arg[j] = k; }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (!(best[j] > 0.f) || !pooled) g[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (vox[k] < 0) continue;
+            float f[4], o[4];
+            unpack4(raw[k], f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float dz = (arg[j] == k) ? g[j] : 0.f;
+                const float xh = (f[j] - mu[j]) * is[j];
+                o[j] = sc[j] * (dz - c1[j] - xh * c2[j]);
+            }
+            st_stream_u2(reinterpret_cast<uint2*>(dy + vox[k] * C) + my_chunk, make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3])));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Pass A without touching y:  the pooled output already carries what the reductions need.
 //   z_argmax = relu-input at the arg-max = p (when p > 0)   =>   xhat_argmax = (p - beta) / gamma
 //   dbeta[c]  = sum_cells dp * [p > 0]          dgamma[c] = sum_cells dp * [p > 0] * (p - beta) / gamma
@@ -465,6 +551,23 @@ __global__ void __launch_bounds__(128) conv1_wgrad_kernel(const __nv_bfloat16* _
     for (int i = threadIdx.x; i < C1_OUT * 27; i += blockDim.x) atomicAdd(&dw[i], s_acc[i]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// One launch packs a conv weight [COUT, CIN, 27] (fp32) into both bf16 GEMM operands:
+//   wf[co, tap*CIN + ci]          (fprop:  y  = conv(x,  W))
+//   wd[ci, (26-tap)*COUT + co]    (dgrad:  dx = conv(dy, flip(W)^T))
+// Row pitches kf / kd are the K extents rounded up to 64; the padding is zeroed once when the buffers are created.
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_conv_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd,
+                                         int cout, int cin, int kf, int kd) {
+    const int total = cout * cin * 27;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tap = i % 27, ci = (i / 27) % cin, co = i / (27 * cin);
+        const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+        wf[(size_t)co * kf + tap * cin + ci] = v;
+        if (wd) wd[(size_t)ci * kd + (26 - tap) * cout + co] = v;
+    }
+}
+
 static inline int grid_for(long long work_items, int threads, int per_thread = 4) {
     long long want = (work_items + (long long)threads * per_thread - 1) / ((long long)threads * per_thread);
     const long long cap = 8LL * B200_SM_COUNT;
@@ -535,8 +638,18 @@ COINN_API int coinn_bn_relu_pool_bwd(const void* y, const void* dp, const float*
     const int grid = (int)(want < 1 ? 1 : (want > 8LL * B200_SM_COUNT ? 8LL * B200_SM_COUNT : want));
     const float inv_count = 1.f / ((float)N * D * H * W);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (apply) bn_relu_pool_bwd_kernel<true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)dp, mean, invstd,
-                                                                   gamma, beta, acc, (__nv_bfloat16*)dy, d, C, inv_count);
+    if (apply) {
+        if (256 % (C / 4) == 0) {                        // 4-channel threads: twice the CTAs per SM
+            const int cpi = 256 / (C / 4);
+            long long w4 = (cells + (long long)cpi * 2 - 1) / ((long long)cpi * 2);
+            const int g4 = (int)(w4 < 1 ? 1 : (w4 > 16LL * B200_SM_COUNT ? 16LL * B200_SM_COUNT : w4));
+            bn_relu_pool_bwd_apply4_kernel<<<g4, 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)dp, mean, invstd, gamma, beta,
+                                                                acc, (__nv_bfloat16*)dy, d, C, inv_count);
+        } else {
+            bn_relu_pool_bwd_kernel<true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)dp, mean, invstd,
+                                                                gamma, beta, acc, (__nv_bfloat16*)dy, d, C, inv_count);
+        }
+    }
     else bn_relu_pool_bwd_kernel<false><<<grid, 256, 2 * C * sizeof(float), st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)dp, mean,
                                                                                    invstd, gamma, beta, acc, nullptr, d, C, inv_count);
     COINN_CHECK_LAUNCH();
@@ -568,6 +681,15 @@ COINN_API int coinn_conv1_wgrad(const void* dy, const void* x, int x_dtype, floa
     const int grid = (int)(want < 1 ? 1 : (want > 8LL * B200_SM_COUNT ? 8LL * B200_SM_COUNT : want));
     if (x_dtype == 0) conv1_wgrad_kernel<float><<<grid, 128, 0, st>>>((const __nv_bfloat16*)dy, (const float*)x, dw, d);
     else conv1_wgrad_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, d);
+    COINN_CHECK_LAUNCH();
+    return 0;
+}
+
+COINN_API int coinn_pack_conv_weights(const float* w, void* wf, void* wd, int cout, int cin, int kf, int kd, void* stream) {
+    const int total = cout * cin * 27;
+    const int grid = (total + 255) / 256 > 592 ? 592 : (total + 255) / 256;
+    coinn::pack_conv_weights_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, cout, cin, kf, kd);
     COINN_CHECK_LAUNCH();
     return 0;
 }

@@ -50,13 +50,16 @@ def conv1_impl(which='fwd'):
 def conv1_fwd(x, weight, impl=None):
     """x: [N,D,H,W] fp32/bf16 (single channel), weight: [16,1,3,3,3] -> (y [N,D,H,W,16] bf16, stats[32])."""
     N, D, H, W = x.shape
-    x = x.float().contiguous()
+    impl = impl or conv1_impl('fwd')
+    if x.dtype == BF16 and impl != 'cuda':
+        impl = 'tc'                                    # bf16 volumes go straight into the tensor-core kernel
+    x = x.contiguous() if (impl == 'tc' and x.dtype in (BF16, _torch.float32)) else x.float().contiguous()
     w = weight.detach().float().reshape(16, 27).contiguous()
     y = _torch.empty((N, D, H, W, 16), dtype=BF16, device=x.device)
     stats = _torch.zeros(32, dtype=_torch.float32, device=x.device)
-    if (impl or conv1_impl('fwd')) == 'tc':
-        _chk(_nat.lib().coinn_conv1_fwd_tc(x.data_ptr(), w.data_ptr(), y.data_ptr(), stats.data_ptr(), N, D, H, W,
-                                           _sp(x)), 'coinn_conv1_fwd_tc')
+    if impl == 'tc':
+        _chk(_nat.lib().coinn_conv1_fwd_tc(x.data_ptr(), 1 if x.dtype == BF16 else 0, w.data_ptr(), y.data_ptr(),
+                                           stats.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_fwd_tc')
     else:
         _chk(_nat.lib().coinn_conv1_fwd(x.data_ptr(), 0, w.data_ptr(), y.data_ptr(),
                                         stats.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_fwd')
@@ -69,9 +72,9 @@ def conv1_wgrad(dy, x, impl=None):
     N, D, H, W = x.shape
     dw = _torch.zeros(16 * 27, dtype=_torch.float32, device=x.device)
     if (impl or conv1_impl('wgrad')) == 'tc':
-        x = x.float().contiguous()
-        _chk(_nat.lib().coinn_conv1_wgrad_tc(dy.contiguous().data_ptr(), x.data_ptr(), dw.data_ptr(), N, D, H, W,
-                                             _sp(x)), 'coinn_conv1_wgrad_tc')
+        x = x.contiguous() if x.dtype in (BF16, _torch.float32) else x.float().contiguous()
+        _chk(_nat.lib().coinn_conv1_wgrad_tc(dy.contiguous().data_ptr(), x.data_ptr(), 1 if x.dtype == BF16 else 0,
+                                             dw.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_wgrad_tc')
     else:
         _chk(_nat.lib().coinn_conv1_wgrad(dy.data_ptr(), x.data_ptr(), 0 if x.dtype == _torch.float32 else 1,
                                           dw.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_wgrad')

@@ -70,7 +70,12 @@ class GraphedStep:
         side.wait_stream(_torch.cuda.current_stream(self.device))
         with _torch.cuda.stream(side):                      # warm-up: lazy inits, cudaFuncSetAttribute, autotune
             for _ in range(2):
-                self._one_step()
+                warm = self._one_step()
+            # the score ring must live OUTSIDE the graph's private pool: a zeros() captured inside the graph
+            # would be re-executed (re-zeroing every row) on each replay
+            width = sum(t.numel() for t in _state_tensors(warm['averages'], warm['metrics'])) or 1
+            if self.ring is None or self.ring.shape[1] != width:
+                self.ring = _torch.zeros(self.ring_len, width, dtype=_torch.float32, device=self.device)
         _torch.cuda.current_stream(self.device).wait_stream(side)
         _torch.cuda.synchronize(self.device)
 
@@ -81,8 +86,6 @@ class GraphedStep:
             it = self._one_step()
             parts = _state_tensors(it['averages'], it['metrics'])
             row = _torch.cat(parts) if parts else _torch.zeros(1, device=self.device)
-            if self.ring is None:
-                self.ring = _torch.zeros(self.ring_len, row.numel(), dtype=_torch.float32, device=self.device)
             self.ring.index_copy_(0, self.cursor % self.ring_len, row.unsqueeze(0))
             self.cursor += 1
         self.kernels_per_replay = _ops.launch_count - before

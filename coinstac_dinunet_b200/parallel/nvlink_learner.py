@@ -148,15 +148,28 @@ class NvlinkLearner(COINNLearner):
             out['fused_steps'] = self.arena.steps_done
             return it, out
         rb = _LaggedReadback(self.device) if self.cache.get('readback_per_step') else None
+        timer = None
+        if self.cache.get('profile'):                     # compspec-style "profile": true -> per-phase device timers
+            from ..utils.profiling import DeviceTimer
+            timer = self.cache.setdefault('_profile_timer', DeviceTimer(self.device if self.device.type == 'cuda' else None))
         for _ in range(self._steps_this_round()):
-            step_its, flags = self.backward()
-            self.arena.reduce_and_step()
+            if timer is not None:
+                with timer('forward_backward'):
+                    step_its, flags = self.backward()
+                with timer('reduce_update'):
+                    self.arena.reduce_and_step()
+            else:
+                step_its, flags = self.backward()
+                self.arena.reduce_and_step()
             if rb is not None:                            # end-to-end mode: every step's loss goes to the host
                 rb.push(step_its[-1]['loss'])
             its.extend(step_its)
         if rb is not None:
             self.cache['last_loss'] = rb.finish()
             self.cache['losses_read'] = rb.count
+        if timer is not None:
+            from ..utils.profiling import site_profile
+            out['profile'] = site_profile(self.cache, timer, key='profile_log')
         # the round IS the epoch: report it finished regardless of where the local cursor is
         self.cache['cursor'] = 0
         out['mode'] = Mode.VALIDATION_WAITING

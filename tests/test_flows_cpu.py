@@ -1,0 +1,94 @@
+"""Secondary protocol flows on CPU: SiteRunner, pre-training + weight broadcast, test-only mode, sparse test
+datasets, the in-memory dataset / pinned collate, user-supplied learner / reducer classes."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from coinstac_dinunet_b200 import COINNLearner, COINNReducer, SiteRunner
+from coinstac_dinunet_b200.data import COINNDataHandle
+from coinstac_dinunet_b200.models import FSVDataset, FSVTrainer, InMemorySynthetic, write_synthetic_site
+from coinstac_dinunet_b200.models.common import pinned_collate
+
+
+def test_site_runner_trains_one_site_offline(tmp_path):
+    data = tmp_path / 'sim'
+    base = data / 'input' / 'local0' / 'simulatorRun'
+    os.makedirs(base)
+    write_synthetic_site(str(base), 40, (66,), seed=0)
+    spec = [{k: {'value': v} for k, v in dict(mode='train', data_dir='data', labels_file='labels.json', num_class=2,
+                                              batch_size=4, epochs=3, split_ratio=[0.6, 0.2, 0.2], learning_rate=1e-2,
+                                              monitor_metric='f1', metric_direction='maximize', patience=5).items()}]
+    with open(data / 'inputspec.json', 'w') as fp:
+        json.dump(spec, fp)
+    runner = SiteRunner('fsv', data_path=str(data), site_index=0)
+    out = runner.run(FSVTrainer, FSVDataset, COINNDataHandle)
+    assert out['phase'] == 'pre_computation'
+    odir = runner.state['outputDirectory']
+    assert os.path.exists(os.path.join(odir, 'fsv', 'splits', 'SPLIT.json'))
+    assert os.path.exists(os.path.join(odir, 'fsv', 'fold_0', 'logs.json'))
+    assert len(runner.cache['train_log']) > 0 and len(runner.cache['validation_log']) == 3
+    assert os.path.exists(os.path.join(odir, 'weights.tar'))          # best pre-training weights in the transfer dir
+
+
+def test_pretraining_broadcasts_weights(fs_sites):
+    eng = fs_sites(spec={'num_folds': None, 'split_ratio': [0.6, 0.2, 0.2], 'epochs': 1})
+    eng.run_nodes(FSVTrainer, FSVDataset, local_kw={'pretrain_args': {'epochs': 2}}, max_rounds=1000)
+    phases = [t['remote'] for t in eng.trace]
+    assert 'pre_computation' in phases and phases[-2] == 'success'
+    # only the site with most training data pre-trains; both then start from its broadcast weights
+    assert os.path.exists(os.path.join(eng.site_state['local1']['baseDirectory'], 'pretrained_weights.tar'))
+    a, b = (torch.cat([p.detach().reshape(-1) for p in eng.site_cache[s]['nn']['fs_net'].parameters()]) for s in eng.site_ids)
+    assert torch.equal(a, b)
+
+
+def test_sparse_test_datasets_and_save_predictions(fs_sites):
+    seen = []
+
+    class T(FSVTrainer):
+        def save_predictions(self, dataset, its):
+            seen.append((len(dataset), type(its['prediction']).__name__))
+            return {}
+    eng = fs_sites(spec={'num_folds': None, 'split_ratio': [0.6, 0.2, 0.2], 'epochs': 1, 'load_sparse': True})
+    eng.run_nodes(T, FSVDataset, max_rounds=1000)
+    assert seen and all(n == 1 for n, _ in seen)                  # one dataset per test subject
+    assert all(kind == '_LazyCollect' for _, kind in seen)        # reduce_iteration hands lazily-collected outputs
+
+
+def test_custom_learner_and_reducer_classes(fs_sites):
+    calls = {'learner': 0, 'reducer': 0}
+
+    class MyLearner(COINNLearner):
+        def to_reduce(self):
+            calls['learner'] += 1
+            return super().to_reduce()
+
+    class MyReducer(COINNReducer):
+        def reduce(self):
+            calls['reducer'] += 1
+            return super().reduce()
+    eng = fs_sites(spec={'num_folds': None, 'split_ratio': [0.6, 0.2, 0.2], 'epochs': 1, 'agg_engine': 'custom'})
+    eng.run_nodes(FSVTrainer, FSVDataset, learner_cls=MyLearner, reducer_cls=MyReducer, max_rounds=1000)
+    assert calls['learner'] > 0 and calls['reducer'] > 0 and eng.trace[-2]['remote'] == 'success'
+
+
+def test_in_memory_dataset_and_pinned_collate():
+    ds = InMemorySynthetic(shape=(3, 4), num_class=2, seed=1, cache={'synthetic_distinct': 8})
+    ds.add([str(i) for i in range(20)])
+    a, b = ds[3], ds[11]                                          # indexes the 8-sample pool modulo
+    assert torch.equal(a['inputs'], b['inputs']) and a['inputs'].shape == (3, 4)
+    batch = pinned_collate([ds[i] for i in range(4, 8)])
+    assert batch['inputs'].shape == (4, 3, 4) and batch['inputs']._base is ds._x    # zero-copy slice
+    mixed = pinned_collate([ds[0], ds[2], ds[5]])
+    assert mixed['inputs'].shape == (3, 3, 4) and torch.equal(mixed['inputs'][1], ds[2]['inputs'])
+
+
+def test_test_only_mode_uses_pretrained_checkpoint(fs_sites, tmp_path):
+    train = fs_sites(spec={'num_folds': None, 'split_ratio': [0.6, 0.2, 0.2], 'epochs': 1})
+    train.run_nodes(FSVTrainer, FSVDataset, max_rounds=1000)
+    ckpt = os.path.join(train.site_state['local0']['outputDirectory'], 'fsv', 'fold_0', 'latest.fsv-0.pt')
+    assert os.path.exists(ckpt)
+    chk = torch.load(ckpt, weights_only=False)
+    assert chk['source'] == 'coinstac' and 'fs_net' in chk['models'] and 'adam' in chk['optimizers']

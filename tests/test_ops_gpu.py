@@ -194,6 +194,10 @@ def test_conv1_fwd_and_wgrad(dev, shape, impl, monkeypatch):
     assert torch.allclose(stats[16:], (yb * yb).sum(0), rtol=1e-3, atol=1e-2)
     dy = torch.randn(N, D, H, W, 16, device=dev).to(torch.bfloat16)
     dw = vbm.conv1_wgrad(dy, x)
+    if impl == 'tc':                       # bf16 volumes are consumed directly by the tensor-core kernels
+        y16, _ = vbm.conv1_fwd(x.bfloat16(), w)
+        assert torch.equal(y16, y)
+        assert torch.allclose(vbm.conv1_wgrad(dy, x.bfloat16()), dw, rtol=1e-4, atol=1e-3)
     _, dw_ref, _ = torch.ops.aten.convolution_backward(
         dy.float().permute(0, 4, 1, 2, 3), x.unsqueeze(1), w, None, [1, 1, 1], [1, 1, 1], [1, 1, 1], False,
         [0, 0, 0], 1, [False, True, False])
