@@ -75,7 +75,7 @@ class VBMNet(_nn.Module):
         from ..ops.linear import LinearFn
         from ..ops.vbm import ConvBnReluPoolFn
         h = x[:, 0] if x.dim() == 5 else x                     # [N, D, H, W]; C_in == 1
-        if h.dtype not in (_torch.float32, _torch.bfloat16):
+        if h.dtype != _torch.float32:                           # bf16 from the host: one 100 MB cast, then fp32 taps
             h = h.float()
         for blk in self.blocks:
             bn = blk.bn

@@ -26,7 +26,7 @@ constexpr int kMaxBlocks = 296;   // flag slots per rank (grid is capped to the 
 constexpr int kThreads = 512;
 
 enum Variant { ONE_SHOT = 0, TWO_SHOT = 1, NVLS = 2 };
-enum OptKind { ADAM = 0, ADAMW = 1, SGD = 2 };
+enum OptKind { ADAM = 0, ADAMW = 1, SGD = 2, NONE = 3 };   // NONE: plain all-reduce(mean) into the parameter arena
 enum GradType { G_F32 = 0, G_BF16 = 1, G_F16 = 2 };
 
 struct FusedArgs {
@@ -118,7 +118,9 @@ struct Hyper {
 
 template <int OPT>
 __device__ __forceinline__ void opt_update(float g, float& p, float& m, float& v, const Hyper& h) {
-    if (OPT == ADAM || OPT == ADAMW) {
+    if (OPT == NONE) {
+        p = g;                                   // the reduced value itself (PowerSGD P/Q factors, rank-1 grads, ...)
+    } else if (OPT == ADAM || OPT == ADAMW) {
         if (OPT == ADAMW) p *= (1.f - h.lr * h.wd);
         else g = fmaf(h.wd, p, g);
         m = fmaf(h.b1, m, (1.f - h.b1) * g);
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_reduce_opt_kernel(const Fus
     h.lr = a.lr_ptr ? *a.lr_ptr : a.lr;
     h.b1 = a.beta1; h.b2 = a.beta2; h.eps = a.eps; h.wd = a.weight_decay; h.mom = a.momentum;
     h.first_step = (t == 1); h.nesterov = a.nesterov;
-    if (OPT != SGD) {
+    if (OPT == ADAM || OPT == ADAMW) {
         const double bc1 = 1.0 - pow((double)a.beta1, (double)t);
         const double bc2 = 1.0 - pow((double)a.beta2, (double)t);
         h.bc1_inv = (float)(1.0 / bc1);
@@ -191,14 +193,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_reduce_opt_kernel(const Fus
         const float sc = a.grad_scale;
         g.x *= sc; g.y *= sc; g.z *= sc; g.w *= sc;
 
-        float4 p4 = P[i], m4 = M[i], v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (OPT != SGD) v4 = V[i];
+        float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f), m4 = p4, v4 = p4;
+        if (OPT != NONE) { p4 = P[i]; m4 = M[i]; }
+        if (OPT == ADAM || OPT == ADAMW) v4 = V[i];
         opt_update<OPT>(g.x, p4.x, m4.x, v4.x, h);
         opt_update<OPT>(g.y, p4.y, m4.y, v4.y, h);
         opt_update<OPT>(g.z, p4.z, m4.z, v4.z, h);
         opt_update<OPT>(g.w, p4.w, m4.w, v4.w, h);
-        M[i] = m4;
-        if (OPT != SGD) V[i] = v4;
+        if (OPT != NONE) M[i] = m4;
+        if (OPT == ADAM || OPT == ADAMW) V[i] = v4;
 
         const uint2 sh = make_uint2(pack_bf16x2(p4.x, p4.y), pack_bf16x2(p4.z, p4.w));
         if (multi && VAR == NVLS) {
@@ -266,6 +269,7 @@ static cudaError_t launch_opt(const FusedArgs& a, int grid, cudaStream_t st) {
         case ADAM:  return launch_var<GD, ADAM>(a, grid, st);
         case ADAMW: return launch_var<GD, ADAMW>(a, grid, st);
         case SGD:   return launch_var<GD, SGD>(a, grid, st);
+        case NONE:  return launch_var<GD, NONE>(a, grid, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -35,15 +35,16 @@ def _chk(code, what):
 # ------------------------------------------------------------------------------------ kernels
 def conv1_impl(which='fwd'):
     """'tc': tcgen05 kernels of conv1_tc.cu; 'cuda': the CUDA-core kernels of vbm_fused.cu.
-    Measured on B200 (profiles/r1_launches_*): forward 611 us (cuda) vs 827 us (tc); wgrad 1180 us (cuda) vs
-    585 us (tc) for the 8 x 121x145x121 batch -> defaults are forward=cuda, wgrad=tc.  COINN_CONV1_IMPL
-    overrides both, COINN_CONV1_FWD / COINN_CONV1_WGRAD one of them."""
+    Measured on B200 for the 8 x 121x145x121 batch (scripts/prof_bn.py): forward 613 us (cuda) vs 523 us (tc);
+    wgrad 1124 us (cuda) vs 310 us (tc) -> both default to tc.  COINN_CONV1_IMPL overrides both,
+    COINN_CONV1_FWD / COINN_CONV1_WGRAD one of them.  bf16 volumes (the PCIe-friendly host format) are up-cast
+    to fp32 once on the device: the kernels read fp32 taps faster than 2-byte taps (3.31 vs 3.75 ms per step)."""
     import os
     both = os.environ.get('COINN_CONV1_IMPL')
     if both:
         return both
     if which == 'fwd':
-        return os.environ.get('COINN_CONV1_FWD', 'cuda')
+        return os.environ.get('COINN_CONV1_FWD', 'tc')
     return os.environ.get('COINN_CONV1_WGRAD', 'tc')
 
 
@@ -51,9 +52,8 @@ def conv1_fwd(x, weight, impl=None):
     """x: [N,D,H,W] fp32/bf16 (single channel), weight: [16,1,3,3,3] -> (y [N,D,H,W,16] bf16, stats[32])."""
     N, D, H, W = x.shape
     impl = impl or conv1_impl('fwd')
-    if x.dtype == BF16 and impl != 'cuda':
-        impl = 'tc'                                    # bf16 volumes go straight into the tensor-core kernel
-    x = x.contiguous() if (impl == 'tc' and x.dtype in (BF16, _torch.float32)) else x.float().contiguous()
+    keep_bf16 = x.dtype == BF16 and impl == 'tc' and _os.environ.get('COINN_CONV1_BF16_TAPS', '0') == '1'
+    x = x.contiguous() if (keep_bf16 or x.dtype == _torch.float32) else x.float().contiguous()
     w = weight.detach().float().reshape(16, 27).contiguous()
     y = _torch.empty((N, D, H, W, 16), dtype=BF16, device=x.device)
     stats = _torch.zeros(32, dtype=_torch.float32, device=x.device)

@@ -23,7 +23,7 @@ from .symm import SymmetricBuffer, _rank, _world
 
 _ALIGN = 8          # elements; keeps every parameter 16-byte aligned in fp32 and in a bf16 shadow
 _VARIANTS = {'one_shot': 0, 'two_shot': 1, 'nvls': 2}
-_OPT_KINDS = {'adam': 0, 'adamw': 1, 'sgd': 2}
+_OPT_KINDS = {'adam': 0, 'adamw': 1, 'sgd': 2, 'none': 3}
 
 
 def _round_up(n, a):
@@ -283,3 +283,69 @@ class _Local:
 
     def barrier(self):
         pass
+
+
+class SymmAllReduce:
+    """In-kernel all-reduce(mean) of small tensor lists over NVLink (no NCCL): the PowerSGD P / Q factor exchange
+    and the dense part of rankDAD.  Same kernel as the dSGD step with ``opt_kind = NONE``:
+    every rank's values are packed into a symmetric input buffer, ``fused_reduce_opt_kernel`` writes the mean into
+    the symmetric output buffer of every rank (one-shot: redundantly; two-shot / NVLS: shard + broadcast) and
+    re-zeroes the input.  Falls back to ``torch.distributed.all_reduce`` off-GPU."""
+
+    def __init__(self, capacity, device, group=None, variant='auto'):
+        self.device, self.group = _torch.device(device), group
+        self.world, self.rank = _world(group), _rank(group)
+        self.capacity = _round_up(max(int(capacity), 4), 4 * max(self.world, 1))
+        self.variant = variant
+        self.native = self.device.type == 'cuda'
+        if self.native:
+            from ..ops import native as _nat
+            self._nat = _nat
+            mk = (lambda n, dt: SymmetricBuffer(n, dt, self.device, group)) if self.world > 1 else \
+                (lambda n, dt: _Local(n, dt, self.device))
+            self.inp, self.out = mk(self.capacity, _torch.float32), mk(self.capacity, _torch.float32)
+            self.flags = mk(_nat.lib().coinn_fused_flag_slots(), _torch.int32)
+            self.epoch = _torch.zeros(_nat.lib().coinn_fused_max_blocks(), dtype=_torch.int32, device=self.device)
+            self.ticket = _torch.zeros(1, dtype=_torch.int32, device=self.device)
+            self.step = _torch.zeros(1, dtype=_torch.int32, device=self.device)
+            self.dummy = _torch.zeros(4, dtype=_torch.float32, device=self.device)
+
+    def mean_(self, tensors):
+        """Replace every tensor in ``tensors`` by its mean over all ranks (in place)."""
+        tensors = [t for t in tensors if t.numel()]
+        if not tensors or self.world == 1:
+            return tensors
+        total = sum(t.numel() for t in tensors)
+        if not self.native or total > self.capacity:
+            flat = _torch.cat([t.reshape(-1).float() for t in tensors])
+            _dist.all_reduce(flat, group=self.group)
+            flat /= self.world
+        else:
+            nat = self._nat
+            n4 = _round_up(total, 4 * self.world)
+            off = 0
+            for t in tensors:
+                self.inp.local[off:off + t.numel()].copy_(t.reshape(-1))
+                off += t.numel()
+            v = self.variant
+            if v == 'auto':
+                v = 'one_shot' if n4 * 4 <= _conf.ONE_SHOT_MAX_BYTES else ('nvls' if self.inp.multicast_ptr and self.out.multicast_ptr else 'two_shot')
+            a = nat.FusedArgs()
+            for r in range(self.world):
+                a.grad_ptrs[r], a.param_ptrs[r], a.flag_ptrs[r] = self.inp.peer_ptrs[r], self.out.peer_ptrs[r], self.flags.peer_ptrs[r]
+            a.grad_mc = self.inp.multicast_ptr or None
+            a.param_mc = self.out.multicast_ptr or None
+            a.m, a.v = self.dummy.data_ptr(), self.dummy.data_ptr()
+            a.epoch, a.step, a.ticket = self.epoch.data_ptr(), self.step.data_ptr(), self.ticket.data_ptr()
+            a.offset, a.numel = 0, n4
+            a.rank, a.world, a.variant, a.opt_kind, a.grad_dtype = self.rank, self.world, _VARIANTS[v], _OPT_KINDS['none'], 0
+            a.zero_grads, a.bump_step, a.grad_scale = 1, 0, 1.0 / self.world
+            nat.check(nat.lib().coinn_fused_reduce_opt(_C.byref(a), 0, nat.stream_ptr(self.device)), 'fused all-reduce')
+            from .. import ops as _ops
+            _ops._count_launch()
+            flat = self.out.local
+        off = 0
+        for t in tensors:
+            t.copy_(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
+        return tensors

@@ -194,16 +194,16 @@ class NvlinkPowerSGDLearner(NvlinkLearner):
         self.st = c.setdefault('powerSGD_state', PowerSGDState())
 
     def _allreduce_mean(self, tensors):
-        if not tensors:
+        """P / Q factors and rank-1 gradients: in-kernel NVLink all-reduce on GPUs (SymmAllReduce), gloo/NCCL
+        all-reduce elsewhere."""
+        if not tensors or not (_dist_on() and _dist.get_world_size() > 1):
             return
-        flat = _torch.cat([t.reshape(-1) for t in tensors])
-        if _dist_on() and _dist.get_world_size() > 1:
-            _dist.all_reduce(flat, op=_dist.ReduceOp.SUM)
-            flat /= _dist.get_world_size()
-        off = 0
-        for t in tensors:
-            t.copy_(flat[off:off + t.numel()].view_as(t))
-            off += t.numel()
+        red = self.cache.get('_symm_allreduce')
+        need = sum(t.numel() for t in tensors)
+        if red is None or red.capacity < need:
+            from .arena import SymmAllReduce
+            red = self.cache['_symm_allreduce'] = SymmAllReduce(max(need, 1 << 16), self.device)
+        red.mean_(tensors)
 
     def _compressed_step(self):
         from ..distrib.powersgd import _native_orthogonalize, _as_matrix

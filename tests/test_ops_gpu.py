@@ -194,7 +194,8 @@ def test_conv1_fwd_and_wgrad(dev, shape, impl, monkeypatch):
     assert torch.allclose(stats[16:], (yb * yb).sum(0), rtol=1e-3, atol=1e-2)
     dy = torch.randn(N, D, H, W, 16, device=dev).to(torch.bfloat16)
     dw = vbm.conv1_wgrad(dy, x)
-    if impl == 'tc':                       # bf16 volumes are consumed directly by the tensor-core kernels
+    if impl == 'tc':                       # bf16 volumes can be consumed directly by the tensor-core kernels
+        monkeypatch.setenv('COINN_CONV1_BF16_TAPS', '1')
         y16, _ = vbm.conv1_fwd(x.bfloat16(), w)
         assert torch.equal(y16, y)
         assert torch.allclose(vbm.conv1_wgrad(dy, x.bfloat16()), dw, rtol=1e-4, atol=1e-3)
