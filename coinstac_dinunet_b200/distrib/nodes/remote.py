@@ -6,6 +6,7 @@ Every transition is gated on *all* sites agreeing (``check(all, key, value, inpu
 the protocol's global barrier.
 """
 import datetime as _datetime
+import json as _json
 import os as _os
 import shutil as _shutil
 import traceback as _tback
@@ -79,6 +80,41 @@ class COINNRemote:
         # a stack: fold 0 is popped first
         self.cache['folds'] = [{'split_ix': str(f), 'seed': self.cache['seed']}
                                for f in reversed(range(self.cache['num_folds']))]
+        self._maybe_resume()
+
+    # ------------------------------------------------------------------ resume
+    def _resume_file(self):
+        return _os.path.join(self.state['outputDirectory'], str(self.cache['task_id']), 'resume.json')
+
+    def _maybe_resume(self):
+        """Fold-level resume (the reference has none): with ``resume=True`` folds recorded as finished
+        by an earlier (crashed / stopped) run over the same output directory are skipped and their test scores are
+        carried into the final cross-fold aggregate."""
+        path = self._resume_file()
+        if not self.cache.get('resume') or not _os.path.exists(path):
+            return
+        with open(path) as fp:
+            done = _json.load(fp)
+        if done.get('seed') is not None:
+            self.cache['seed'] = done['seed']
+        finished = set(done.get('completed_folds', []))
+        self.cache['folds'] = [f for f in self.cache['folds'] if f['split_ix'] not in finished]
+        for f in self.cache['folds']:
+            f['seed'] = self.cache['seed']
+        self.cache[Key.GLOBAL_TEST_SERIALIZABLE] = list(done.get('global_test_serializable', []))
+        self.cache['resumed_folds'] = sorted(finished)
+
+    def _record_fold_done(self):
+        path = self._resume_file()
+        _os.makedirs(_os.path.dirname(path), exist_ok=True)
+        prev = {'completed_folds': []}
+        if _os.path.exists(path):
+            with open(path) as fp:
+                prev = _json.load(fp)
+        folds = list(dict.fromkeys(list(prev.get('completed_folds', [])) + [self.cache['fold']['split_ix']]))
+        with open(path, 'w') as fp:
+            _json.dump({'completed_folds': folds, 'seed': self.cache.get('seed'),
+                        'global_test_serializable': self.cache[Key.GLOBAL_TEST_SERIALIZABLE]}, fp)
 
     def _next_run(self, trainer):
         """Pop the next fold, reset epoch/score/log state, tell each site its fold, seed and
@@ -138,6 +174,7 @@ class COINNRemote:
         snapshot = {**self.cache}
         snapshot[Key.GLOBAL_TEST_SERIALIZABLE] = snapshot[Key.GLOBAL_TEST_SERIALIZABLE][-1]
         _utils.save_cache(snapshot, self.cache['log_dir'])
+        self._record_fold_done()
 
     def _send_global_scores(self, trainer):
         """All folds done: cross-fold score, ``global_test_metrics.csv`` and the results zip."""
@@ -173,8 +210,12 @@ class COINNRemote:
 
         if check(all, 'phase', Phase.INIT_RUNS, self.input):
             self._init_runs()
-            self.out['global_runs'] = self._next_run(trainer)
-            self.out['phase'] = Phase.NEXT_RUN
+            if len(self.cache['folds']) > 0:
+                self.out['global_runs'] = self._next_run(trainer)
+                self.out['phase'] = Phase.NEXT_RUN
+            else:                                   # resumed run with nothing left to train
+                self.out.update(**self._send_global_scores(trainer))
+                self.out['phase'] = Phase.SUCCESS
 
         if check(all, 'phase', Phase.PRE_COMPUTATION, self.input):
             self.out.update(**self._pre_compute())

@@ -43,3 +43,31 @@ def test_node_exception_carries_last_output(fs_sites):
     with pytest.raises(Exception) as exc:
         eng.run_nodes(Broken, FSVDataset, max_rounds=50)
     assert 'phase' in str(exc.value)
+
+
+def test_fold_level_resume(fs_sites, tmp_path):
+    """A run that dies after fold 0 is restarted with fresh node caches and ``resume=True``: finished folds are
+    skipped, the final aggregate still covers all three folds."""
+    import os
+    spec = {'num_folds': 3, 'epochs': 1}
+    eng = fs_sites(spec=spec)
+
+    def stop_after_first_fold(rnd, site):
+        if sum(t['remote'] == 'next_run' for t in eng.trace) >= 2:      # fold 0 done, fold 1 announced
+            raise KeyboardInterrupt('power cut')
+    eng.fault_hook = stop_after_first_fold
+    with pytest.raises(KeyboardInterrupt):
+        eng.run_nodes(FSVTrainer, FSVDataset, max_rounds=2000)
+    resume_file = os.path.join(eng.remote_state['outputDirectory'], 'fsv', 'resume.json')
+    assert os.path.exists(resume_file)
+
+    from coinstac_dinunet_b200.engine import InProcessEngine
+    base = dict(task_id='fsv', mode='train', data_dir='data', labels_file='labels.json', input_size=66, num_class=2,
+                batch_size=4, learning_rate=1e-2, seed=7, monitor_metric='f1', metric_direction='maximize',
+                log_header='Loss|Accuracy,F1', verbose=False, **spec)
+    eng2 = InProcessEngine(eng.work_dir, n_sites=2, inputspec=base)      # same directories, empty caches
+    eng2.run_nodes(FSVTrainer, FSVDataset, remote_kw={'resume': True}, max_rounds=2000)
+    assert eng2.remote_cache['resumed_folds'] == ['0']
+    assert [t['remote'] for t in eng2.trace].count('next_run') == 2      # only folds 1 and 2 were trained
+    rows = open(os.path.join(eng2.remote_state['outputDirectory'], 'fsv', 'global_test_metrics.csv')).read().strip().split('\n')
+    assert len(rows) == 2 and len(eng2.remote_cache['serializable_global_test_scores']) == 3
