@@ -11,6 +11,7 @@
 // The 27*CIN x COUT weight matrix is loaded once per (persistent) CTA and stays in shared memory.
 // Output rows at the two padding columns of every line are computed and discarded (2/(W+2) waste).
 #include "umma.cuh"
+#include <cstdlib>
 
 namespace coinn {
 
@@ -34,7 +35,7 @@ __device__ __forceinline__ void tma_load_5d_h(void* smem_dst, const CUtensorMap*
 }
 
 template <int CIN, int COUT, bool FULLPIX>
-__global__ void __launch_bounds__(CH_THREADS, 1)
+__global__ void __launch_bounds__(CH_THREADS, 2)
 conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const ConvHaloParams p) {
     // FULLPIX: one box per d-plane holding whole pixels (CIN*2 = 32/64 bytes, 32B/64B swizzle) - 2-4x fewer and
     // 2-4x larger TMA requests than the chunk-plane layout (8 channels = 16 B per request, no swizzle).
@@ -209,7 +210,13 @@ static int launch_conv_halo(const void* x, const void* wk, void* y, int N, int D
     p.region_tx = (uint32_t)(p.TH + 2) * p.Wp * (uint32_t)PIXB;
     p.region_bytes = (p.region_tx + 1023u) & ~1023u;          // 1 KB: keeps swizzle phases of the regions identical
     const uint32_t stage_bytes = REGIONS * p.region_bytes + 1024;
-    const int budget = 220 * 1024 - (int)W_BYTES - 1024 - 512;
+    // two CTAs per SM (each with its own MMA-issue thread, TMA queue and epilogue) when there are plenty of tiles and
+    // the weights + 3 halo stages fit twice: the per-tile latency chains of the two CTAs overlap
+    static int ctas_env = -1;
+    if (ctas_env < 0) { const char* e = getenv("COINN_HALO_CTAS"); ctas_env = e ? atoi(e) : 2; }
+    int ctas = (ctas_env >= 2 && p.num_tiles >= 4 * B200_SM_COUNT && 2 * COUT * 2 <= 256 &&
+                (int)W_BYTES + 3 * (int)stage_bytes + 2048 <= 110 * 1024) ? 2 : 1;
+    const int budget = (ctas == 2 ? 110 : 220) * 1024 - (int)W_BYTES - 1024 - 512;
     int stages = budget / (int)stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) return -1;
@@ -235,7 +242,7 @@ static int launch_conv_halo(const void* x, const void* wk, void* y, int N, int D
         if (e != cudaSuccess) return (int)e;
         configured = smem_bytes;
     }
-    const int grid = p.num_tiles < B200_SM_COUNT ? p.num_tiles : B200_SM_COUNT;
+    const int grid = p.num_tiles < ctas * B200_SM_COUNT ? p.num_tiles : ctas * B200_SM_COUNT;
     conv3d_halo_kernel<CIN, COUT, FULLPIX><<<grid, CH_THREADS, smem_bytes, st>>>(tx, tw, p);
     COINN_CHECK_LAUNCH();
     return 0;
