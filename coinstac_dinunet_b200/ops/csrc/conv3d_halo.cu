@@ -213,7 +213,7 @@ static int launch_conv_halo(const void* x, const void* wk, void* y, int N, int D
     // two CTAs per SM (each with its own MMA-issue thread, TMA queue and epilogue) when there are plenty of tiles and
     // the weights + 3 halo stages fit twice: the per-tile latency chains of the two CTAs overlap
     static int ctas_env = -1;
-    if (ctas_env < 0) { const char* e = getenv("COINN_HALO_CTAS"); ctas_env = e ? atoi(e) : 2; }
+    if (ctas_env < 0) { const char* e = getenv("COINN_HALO_CTAS"); ctas_env = e ? atoi(e) : 1; }   // measured: 2 CTAs/SM 161 us vs 1 CTA 154 us (layer-2 fprop): no gain
     int ctas = (ctas_env >= 2 && p.num_tiles >= 4 * B200_SM_COUNT && 2 * COUT * 2 <= 256 &&
                 (int)W_BYTES + 3 * (int)stage_bytes + 2048 <= 110 * 1024) ? 2 : 1;
     const int budget = (ctas == 2 ? 110 : 220) * 1024 - (int)W_BYTES - 1024 - 512;

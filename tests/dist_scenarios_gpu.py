@@ -53,4 +53,29 @@ def scenario_fused(work, opts):
             json.dump({'results': results, 'world': world}, fp)
 
 
-SCENARIOS = {'fused': scenario_fused}
+def scenario_allreduce(work, opts):
+    """SymmAllReduce (fused kernel with opt_kind NONE) vs torch.distributed.all_reduce, all variants."""
+    from coinstac_dinunet_b200.parallel.arena import SymmAllReduce
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    results = []
+    for variant in ('one_shot', 'two_shot', 'nvls'):
+        red = SymmAllReduce(1 << 18, dev, variant=variant)
+        for shapes in ([(5,), (3, 7)], [(1000, 33)], [(64, 1), (1,), (17, 17, 3)]):
+            g = torch.Generator(device='cpu').manual_seed(rank * 100 + len(shapes))
+            ts = [torch.randn(*s, generator=g).to(dev) for s in shapes]
+            want = [t.clone() for t in ts]
+            for t in want:
+                dist.all_reduce(t)
+                t /= world
+            for rep in range(3):                                   # repeated use: buffers are re-zeroed by the kernel
+                got = [t.clone() for t in ts]
+                red.mean_(got)
+            err = max(float((a - b).abs().max()) for a, b in zip(got, want))
+            results.append({'variant': variant, 'err': err})
+    if rank == 0:
+        with open(os.path.join(work, 'result.json'), 'w') as fp:
+            json.dump({'results': results, 'world': world}, fp)
+
+
+SCENARIOS = {'fused': scenario_fused, 'allreduce': scenario_allreduce}

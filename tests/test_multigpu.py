@@ -24,3 +24,13 @@ def test_fused_reduce_all_variants(tmp_path):
 def test_protocol_over_nvlink(tmp_path):
     res = run_workers('protocol', tmp_path, nproc=_n(), port=29702, extra=['transport=nvlink'])
     assert res['backend'] == 'nvlink' and res['replicas_identical'] and res['csv']
+
+
+def test_symm_allreduce_matches_nccl(tmp_path):
+    res = run_workers('allreduce', tmp_path, nproc=_n(), port=29703)
+    assert all(r['err'] < 1e-5 for r in res['results']), res
+
+
+def test_powersgd_protocol_over_nvlink(tmp_path):
+    res = run_workers('protocol', tmp_path, nproc=_n(), port=29704, extra=['transport=nvlink', 'agg_engine=powerSGD'])
+    assert res['backend'] == 'nvlink' and res['csv'] and res['trace'][-2] == 'success'

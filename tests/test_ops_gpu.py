@@ -365,3 +365,25 @@ def test_cuda_graph_replay_bit_equals_eager(dev):
     assert abs(float(avg.get()[0]) - sum(losses) / len(losses)) < 1e-4
     assert met.tp + met.tn == tp and met.tp + met.tn + met.fp + met.fn == 48
     assert int(a2.step_count) == 6 and gs.kernels_per_replay >= 3
+
+
+def test_pack_conv_weights_kernel_matches_torch_packs(dev):
+    """one-launch bf16 weight packing (fprop + dgrad layouts) vs the reference torch permutations."""
+    from coinstac_dinunet_b200.ops import conv3d
+    torch.manual_seed(0)
+    for cout, cin in ((32, 16), (64, 32), (256, 128)):
+        w = torch.randn(cout, cin, 3, 3, 3, device=dev)
+        wf, kf, wd, kd = conv3d.pack_weights(w)
+        rf, kf_ref = conv3d.pack_fprop_weight(w)
+        rd, kd_ref = conv3d.pack_dgrad_weight(w)
+        assert (kf, kd) == (kf_ref, kd_ref)
+        assert torch.equal(wf, rf) and torch.equal(wd, rd)
+
+
+def test_symm_allreduce_single_rank_is_identity(dev):
+    from coinstac_dinunet_b200.parallel.arena import SymmAllReduce
+    red = SymmAllReduce(1000, dev)
+    ts = [torch.randn(7, 3, device=dev), torch.randn(11, device=dev)]
+    want = [t.clone() for t in ts]
+    red.mean_(ts)
+    assert all(torch.equal(a, b) for a, b in zip(ts, want))
