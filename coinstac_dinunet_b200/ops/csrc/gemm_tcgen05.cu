@@ -215,5 +215,9 @@ COINN_API int coinn_gemm_bf16_tn(const void* A, const void* B, void* C, const fl
     if (N <= 16) return launch_gemm<16>(A, B, p, lda, ldb, split_k, st);
     if (N <= 32) return launch_gemm<32>(A, B, p, lda, ldb, split_k, st);
     if (N <= 64) return launch_gemm<64>(A, B, p, lda, ldb, split_k, st);
+    // 128 x 256 tiles double the MMA work per byte of shared-memory operand traffic (the N=128 kernel sits at 44 % tensor
+    // pipe, bound by operand fetch); use them when they still fill the machine
+    const long long tiles256 = (long long)((M + GEMM_BM - 1) / GEMM_BM) * ((N + 255) / 256) * split_k;
+    if (N >= 256 && tiles256 >= B200_SM_COUNT) return launch_gemm<256>(A, B, p, lda, ldb, split_k, st);
     return launch_gemm<128>(A, B, p, lda, ldb, split_k, st);
 }

@@ -92,3 +92,14 @@ def test_test_only_mode_uses_pretrained_checkpoint(fs_sites, tmp_path):
     assert os.path.exists(ckpt)
     chk = torch.load(ckpt, weights_only=False)
     assert chk['source'] == 'coinstac' and 'fs_net' in chk['models'] and 'adam' in chk['optimizers']
+
+
+def test_example_computations_run_in_the_simulator():
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('run_simulator', os.path.join(root, 'examples', 'run_simulator.py'))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    eng = sim.main('fsv')
+    assert eng.trace[-2]['remote'] == 'success'
+    assert json.load(open(os.path.join(root, 'examples', 'vbm', 'compspec.json')))['computation']['input']['transport']['default'] == 'nvlink'
