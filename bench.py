@@ -45,6 +45,7 @@ def parse():
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--transport', default='nvlink', choices=['nvlink', 'nccl'])
     ap.add_argument('--variant', default='auto', choices=['auto', 'one_shot', 'two_shot', 'nvls'])
+    ap.add_argument('--overlap', type=int, default=0, help='bucketed reduce+update launched from grad hooks during backward')
     ap.add_argument('--native', type=int, default=1, help='use the hand-written sm_100a model kernels')
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--input-dtype', default='bf16', choices=['bf16', 'fp32'],
@@ -237,7 +238,7 @@ def run_ours(a):
                        else 'FSNet MLP 66-256-128-64-32-2',
                        'input': list(shape), 'per_site_batch': batch, 'global_batch': batch * a.gpus,
                        'parallelism': f'dSGD sites={a.gpus} (1 site/GPU)', 'optimizer': 'Adam(1e-3)',
-                       'transport': arena.backend, 'reduce_variant': arena._pick_variant(arena.numel * 4),
+                       'transport': arena.backend, 'reduce_variant': arena._pick_variant(arena.numel * 4), 'overlap_backward': bool(a.overlap),
                        'native_model_kernels': bool(a.native), 'cuda_graph': bool(a.graph),
                        'host_input_dtype': a.input_dtype if a.model == 'vbm' else 'fp32',
                        'l2_policy': 'inputs rotate over 4 distinct batches; activations per step >> 126 MB L2'},

@@ -245,6 +245,9 @@ class DistArena:
         self.steps_done += 1
         self.host_step += 1
         if self.backend == 'nvlink':
+            if getattr(self, '_overlap', None) and self._overlap['armed']:
+                self._finish_overlap()
+                return 'bucketed'
             return self._launch(self.world, 1.0 / self.world, zero_grads)
         if self.backend == 'nccl':
             if self.world > 1:
@@ -259,6 +262,74 @@ class DistArena:
         if zero_grads:
             self.flat_grad.zero_()
         return 'torch'
+
+    # ---------------------------------------------------------------- backward overlap (bucketed)
+    def enable_overlap(self, bucket_bytes=4 << 20):
+        """Launch the fused reduce+update per *bucket* as soon as autograd has produced the bucket's last gradient
+        (``register_post_accumulate_grad_hook``), on a side stream, so the cross-GPU exchange of the late layers
+        overlaps the backward pass of the early ones.  Buckets are contiguous arena ranges covering
+        whole parameters; they complete in reverse parameter order.  ``reduce_and_step()`` then only launches what
+        is left and joins the streams.  Only meaningful for the ``nvlink`` backend."""
+        if self.backend != 'nvlink' or getattr(self, '_overlap', None):
+            return self
+        cap = max(int(bucket_bytes) // 4, 4 * max(self.world, 1))
+        buckets, start, members = [], 0, []
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            end = off + _round_up(p.numel(), _ALIGN)
+            members.append(i)
+            if end - start >= cap or i == len(self.params) - 1:
+                stop = self.numel if i == len(self.params) - 1 else end
+                buckets.append({'offset': start, 'numel': stop - start, 'params': members, 'pending': len(members)})
+                start, members = end, []
+        self._overlap = {'buckets': buckets, 'armed': False, 'launched': set(),
+                         'stream': _torch.cuda.Stream(self.device), 'owner': {}}
+        for b_ix, b in enumerate(buckets):
+            for i in b['params']:
+                self._overlap['owner'][i] = b_ix
+        for i, p in enumerate(self.params):
+            p.register_post_accumulate_grad_hook(lambda _p, ix=i: self._grad_ready(ix))
+        return self
+
+    def arm_overlap(self):
+        """Call before the LAST micro-batch's backward of a step (earlier micro-batches only accumulate)."""
+        ov = getattr(self, '_overlap', None)
+        if ov:
+            ov['armed'] = True
+            ov['launched'] = set()
+            for b in ov['buckets']:
+                b['pending'] = len(b['params'])
+
+    def _launch_bucket(self, b_ix, last):
+        ov, nat = self._overlap, self._nat
+        b = ov['buckets'][b_ix]
+        variant = self._pick_variant(b['numel'] * 4) if self.world > 1 else 'one_shot'
+        a = self._fused_args(b['offset'], b['numel'], variant, self.world, 1.0 / self.world, True, bool(last))
+        cur = _torch.cuda.current_stream(self.device)
+        ov['stream'].wait_stream(cur)                   # the bucket's gradients were produced on the compute stream
+        with _torch.cuda.stream(ov['stream']):
+            nat.check(nat.lib().coinn_fused_reduce_opt(_C.byref(a), 0, nat.stream_ptr(self.device)),
+                      'coinn_fused_reduce_opt[bucket]')
+        from .. import ops as _ops
+        _ops._count_launch()
+        ov['launched'].add(b_ix)
+
+    def _grad_ready(self, param_ix):
+        ov = self._overlap
+        if not ov['armed']:
+            return
+        b_ix = ov['owner'][param_ix]
+        b = ov['buckets'][b_ix]
+        b['pending'] -= 1
+        if b['pending'] == 0 and len(ov['launched']) < len(ov['buckets']) - 1:
+            self._launch_bucket(b_ix, last=False)       # the final bucket is launched by reduce_and_step (bumps the step)
+
+    def _finish_overlap(self):
+        ov = self._overlap
+        rest = [i for i in range(len(ov['buckets'])) if i not in ov['launched']]
+        for k, b_ix in enumerate(rest):
+            self._launch_bucket(b_ix, last=(k == len(rest) - 1))
+        _torch.cuda.current_stream(self.device).wait_stream(ov['stream'])
+        ov['armed'] = False
 
     def local_step(self, zero_grads=True):
         """Optimizer step on the local gradients only (pre-training / single site)."""

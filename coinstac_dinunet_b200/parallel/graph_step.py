@@ -48,6 +48,7 @@ class GraphedStep:
     # --------------------------------------------------------------------------------- capture
     def _one_step(self):
         it = self.trainer.iteration(self.static)
+        self.arena.arm_overlap()
         it['loss'].backward()
         self.arena.reduce_and_step()
         return it

@@ -66,6 +66,7 @@ class _LaggedReadback:
 
 
 class NvlinkLearner(COINNLearner):
+    _overlap_ok = True      # bucket kernels from grad hooks only make sense when reduce+update is the fused kernel
     @property
     def arena(self):
         """The flat arenas + fused optimizer of this site; built on first use (the learner object
@@ -79,6 +80,8 @@ class NvlinkLearner(COINNLearner):
             arena = DistArena(self.model, self.optim, device=self.device, backend=backend,
                               variant=self.cache.get('reduce_variant', 'auto'),
                               shadow_bf16=bool(self.cache.get('shadow_bf16', False)))
+            if self.cache.get('overlap_backward') and self._overlap_ok:
+                arena.enable_overlap(int(self.cache.get('bucket_bytes', 4 << 20)))
             self.cache['_arena'] = arena
         return arena
 
@@ -105,9 +108,12 @@ class NvlinkLearner(COINNLearner):
         out, its = {}, []
         self.model.train()
         self.arena.rebind_grads()
-        for _ in range(self.cache.get('local_iterations', 1)):
+        k = self.cache.get('local_iterations', 1)
+        for i in range(k):
             batch, flags = self.trainer.data_handle.next_iter()
             it = self.trainer.iteration(batch)
+            if i == k - 1 and self._overlap_ok:
+                self.arena.arm_overlap()               # bucket kernels may start as soon as their gradients are final
             it['loss'].backward()
             its.append(it)
             out.update(**flags)
@@ -181,6 +187,7 @@ class NvlinkPowerSGDLearner(NvlinkLearner):
     """PowerSGD over the device collectives (P/Q factors all-reduced instead of shipped as files).
     Math as in ``distrib.powersgd`` (rank-r, error feedback, warm start); the two reductions per
     step are ``torch.distributed`` all-reduces of the small factor buffers."""
+    _overlap_ok = False
 
     def __init__(self, **kw):
         super().__init__(**kw)
@@ -259,6 +266,7 @@ class NvlinkDADLearner(NvlinkLearner):
     """rankDAD over device collectives: per-layer (delta, activation) factors are all-gathered,
     concatenated along the rank axis and re-compressed on every site (deterministically, so the
     replicas agree), then turned back into dense gradients for the fused local step."""
+    _overlap_ok = False
 
     def __init__(self, **kw):
         from ..distrib.rankdad.spi import DADParallel

@@ -78,4 +78,42 @@ def scenario_allreduce(work, opts):
             json.dump({'results': results, 'world': world}, fp)
 
 
-SCENARIOS = {'fused': scenario_fused, 'allreduce': scenario_allreduce}
+def scenario_overlap(work, opts):
+    """bucketed launch from grad hooks (side stream, during backward) vs one launch after backward."""
+    from coinstac_dinunet_b200.parallel.arena import DistArena
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    results = []
+    for variant in ('one_shot', 'two_shot', 'auto'):
+        torch.manual_seed(5)
+        mk = lambda: torch.nn.Sequential(torch.nn.Linear(257, 600), torch.nn.ReLU(), torch.nn.Linear(600, 300),
+                                         torch.nn.ReLU(), torch.nn.Linear(300, 5)).to(dev)
+        m1, m2 = mk(), mk()
+        m2.load_state_dict(m1.state_dict())
+        a1 = DistArena(m1, torch.optim.Adam(m1.parameters(), lr=1e-2), device=dev, backend='nvlink', variant=variant)
+        a2 = DistArena(m2, torch.optim.Adam(m2.parameters(), lr=1e-2), device=dev, backend='nvlink', variant=variant)
+        a2.enable_overlap(bucket_bytes=128 << 10)
+        for step in range(6):
+            g = torch.Generator(device='cpu').manual_seed(77 * step + rank)
+            x = torch.randn(16, 257, generator=g).to(dev)
+            m1(x).square().mean().backward()
+            a1.reduce_and_step()
+            if (step + rank) % 2:
+                time.sleep(0.005 * (rank + 1))
+            a2.arm_overlap()
+            m2(x).square().mean().backward()
+            how = a2.reduce_and_step()
+        torch.cuda.synchronize()
+        err = float((a1.flat_param - a2.flat_param).abs().max())
+        mine = a2.flat_param.clone()
+        allp = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allp, mine)
+        results.append({'variant': variant, 'how': how, 'err': err, 'buckets': len(a2._overlap['buckets']),
+                        'identical': all(torch.equal(allp[0], q) for q in allp[1:]),
+                        'steps': int(a2.step_count), 'zeroed': float(a2.flat_grad.abs().max()) == 0.0})
+    if rank == 0:
+        with open(os.path.join(work, 'result.json'), 'w') as fp:
+            json.dump({'results': results, 'world': world}, fp)
+
+
+SCENARIOS = {'fused': scenario_fused, 'allreduce': scenario_allreduce, 'overlap': scenario_overlap}

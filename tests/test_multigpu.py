@@ -34,3 +34,10 @@ def test_symm_allreduce_matches_nccl(tmp_path):
 def test_powersgd_protocol_over_nvlink(tmp_path):
     res = run_workers('protocol', tmp_path, nproc=_n(), port=29704, extra=['transport=nvlink', 'agg_engine=powerSGD'])
     assert res['backend'] == 'nvlink' and res['csv'] and res['trace'][-2] == 'success'
+
+
+def test_bucketed_overlap_matches_single_launch(tmp_path):
+    res = run_workers('overlap', tmp_path, nproc=_n(), port=29705)
+    for r in res['results']:
+        assert r['how'] == 'bucketed' and r['buckets'] >= 3 and r['steps'] == 6, r
+        assert r['err'] < 1e-6 and r['identical'] and r['zeroed'], r

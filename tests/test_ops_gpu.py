@@ -387,3 +387,26 @@ def test_symm_allreduce_single_rank_is_identity(dev):
     want = [t.clone() for t in ts]
     red.mean_(ts)
     assert all(torch.equal(a, b) for a, b in zip(ts, want))
+
+
+def test_bucketed_backward_overlap_equals_single_launch(dev):
+    """per-bucket fused kernels launched from grad hooks on a side stream == one launch after backward."""
+    from coinstac_dinunet_b200.parallel.arena import DistArena
+    def make():
+        torch.manual_seed(9)
+        m = torch.nn.Sequential(torch.nn.Linear(300, 500), torch.nn.ReLU(), torch.nn.Linear(500, 400), torch.nn.ReLU(),
+                                torch.nn.Linear(400, 7)).to(dev)
+        return m, torch.optim.Adam(m.parameters(), lr=1e-2)
+    (m1, o1), (m2, o2) = make(), make()
+    a1 = DistArena(m1, o1, device=dev, backend='nvlink')
+    a2 = DistArena(m2, o2, device=dev, backend='nvlink').enable_overlap(bucket_bytes=256 << 10)
+    assert len(a2._overlap['buckets']) >= 3
+    for step in range(5):
+        x = torch.randn(32, 300, device=dev)
+        m1(x).square().mean().backward(); a1.reduce_and_step()
+        a2.arm_overlap(); m2(x).square().mean().backward()
+        assert a2.reduce_and_step() == 'bucketed'
+    torch.cuda.synchronize()
+    assert torch.equal(a1.flat_param, a2.flat_param) and torch.equal(a1.m, a2.m)
+    assert int(a1.step_count) == int(a2.step_count) == 5
+    assert float(a2.flat_grad.abs().max()) == 0.0
