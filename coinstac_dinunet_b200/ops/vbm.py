@@ -10,6 +10,7 @@ MaxPool3d(2).  Passes over HBM per block:
 versus conv, BN-stat, BN-apply, ReLU, pool (each a full read+write) in the PyTorch chain - whose
 channels-last-3d BatchNorm backward alone takes 40 ms per step on a B200 (profiles/r1_launches_torch.txt).
 """
+import ctypes as _C
 import os as _os
 
 import torch as _torch
@@ -44,14 +45,37 @@ def conv1_impl(which='fwd'):
     if both:
         return both
     if which == 'fwd':
-        return os.environ.get('COINN_CONV1_FWD', 'tc')
+        return os.environ.get('COINN_CONV1_FWD', 'toeplitz')
     return os.environ.get('COINN_CONV1_WGRAD', 'tc')
 
 
-def conv1_fwd(x, weight, impl=None):
+def conv1_pad_input(x):
+    """[N,D,H,W] fp32/bf16 volume -> zero-padded bf16 row matrix [N*(D+2)*(H+2), Wq] that the banded-Toeplitz
+    tcgen05 kernels (conv1_toeplitz.cu) read by TMA; one pass over the input (replaces the bf16->fp32 up-cast)."""
+    N, D, H, W = x.shape
+    x = x.contiguous() if x.dtype in (BF16, _torch.float32) else x.float().contiguous()
+    rows, cols = _C.c_longlong(0), _C.c_int(0)
+    _nat.lib().coinn_conv1_padded_shape(N, D, H, W, _C.byref(rows), _C.byref(cols))
+    xp = _torch.empty((rows.value, cols.value), dtype=BF16, device=x.device)
+    _chk(_nat.lib().coinn_conv1_pad_input(x.data_ptr(), 1 if x.dtype == BF16 else 0, xp.data_ptr(), N, D, H, W, _sp(x)),
+         'coinn_conv1_pad_input')
+    _bump()
+    return xp
+
+
+def conv1_fwd(x, weight, impl=None, xp=None):
     """x: [N,D,H,W] fp32/bf16 (single channel), weight: [16,1,3,3,3] -> (y [N,D,H,W,16] bf16, stats[32])."""
     N, D, H, W = x.shape
     impl = impl or conv1_impl('fwd')
+    if impl == 'toeplitz':
+        xp = conv1_pad_input(x) if xp is None else xp
+        w = weight.detach().float().reshape(16, 27).contiguous()
+        y = _torch.empty((N, D, H, W, 16), dtype=BF16, device=x.device)
+        stats = _torch.zeros(32, dtype=_torch.float32, device=x.device)
+        _chk(_nat.lib().coinn_conv1_fwd_toeplitz(xp.data_ptr(), w.data_ptr(), y.data_ptr(), stats.data_ptr(), N, D, H, W, _sp(x)),
+             'coinn_conv1_fwd_toeplitz')
+        _bump()
+        return y, stats
     keep_bf16 = x.dtype == BF16 and impl == 'tc' and _os.environ.get('COINN_CONV1_BF16_TAPS', '0') == '1'
     x = x.contiguous() if (keep_bf16 or x.dtype == _torch.float32) else x.float().contiguous()
     w = weight.detach().float().reshape(16, 27).contiguous()

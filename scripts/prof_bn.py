@@ -22,7 +22,11 @@ def timeit(name, fn, n=5):
     e1.record(); torch.cuda.synchronize()
     print(f'{name:28s} {e0.elapsed_time(e1) / n * 1e3:8.1f} us')
 
-if len(sys.argv) > 1 and sys.argv[1] == 'prof':
+if len(sys.argv) > 1 and sys.argv[1] == 'prof_t':
+    xp = vbm.conv1_pad_input(x)
+    vbm.conv1_fwd(x, w, impl='toeplitz', xp=xp)
+    torch.cuda.synchronize()
+elif len(sys.argv) > 1 and sys.argv[1] == 'prof':
     dy, dg, db = vbm.bn_relu_pool_bwd(y, dp, mean, invstd, gamma, beta)
     vbm.conv1_wgrad(dy, x)
     vbm.conv1_fwd(x, w)
@@ -30,6 +34,10 @@ if len(sys.argv) > 1 and sys.argv[1] == 'prof':
 else:
     timeit('conv1_fwd[cuda]', lambda: vbm.conv1_fwd(x, w, impl='cuda'))
     timeit('conv1_fwd[tc]', lambda: vbm.conv1_fwd(x, w, impl='tc'))
+    timeit('conv1_pad_input', lambda: vbm.conv1_pad_input(x))
+    xp = vbm.conv1_pad_input(x)
+    timeit('conv1_fwd[toeplitz] (no pad)', lambda: vbm.conv1_fwd(x, w, impl='toeplitz', xp=xp))
+    if len(sys.argv) > 1 and sys.argv[1] == 'fwdonly': sys.exit(0)
     timeit('bn_relu_pool_fwd', lambda: vbm.bn_relu_pool_fwd(y, mean, invstd, gamma, beta))
     timeit('bn_relu_pool_bwd (A+B)', lambda: vbm.bn_relu_pool_bwd(y, dp, mean, invstd, gamma, beta))
     dy, _, _ = vbm.bn_relu_pool_bwd(y, dp, mean, invstd, gamma, beta)

@@ -410,3 +410,25 @@ def test_bucketed_backward_overlap_equals_single_launch(dev):
     assert torch.equal(a1.flat_param, a2.flat_param) and torch.equal(a1.m, a2.m)
     assert int(a1.step_count) == int(a2.step_count) == 5
     assert float(a2.flat_grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('shape', [(2, 9, 11, 13), (1, 5, 140, 30), (2, 3, 4, 121), (1, 20, 9, 64)])
+def test_conv1_toeplitz_fwd(dev, shape):
+    """banded-Toeplitz tcgen05 conv1 (W axis as GEMM K, TMA chunk planes) vs torch conv3d on bf16-rounded operands."""
+    from coinstac_dinunet_b200.ops import vbm
+    torch.manual_seed(3)
+    N, D, H, W = shape
+    x = torch.randn(N, D, H, W, device=dev).bfloat16().float()
+    w = (torch.randn(16, 1, 3, 3, 3, device=dev) * 0.2).bfloat16().float()
+    xp = vbm.conv1_pad_input(x)
+    rows = xp.view(N, D + 2, H + 2, -1)
+    assert torch.equal(rows[:, 1:-1, 1:-1, 1:W + 1].float(), x) and float(rows[:, 0].abs().max()) == 0
+    assert float(rows[..., 0].abs().max()) == 0 and float(rows[..., W + 1:].abs().max()) == 0
+    y, stats = vbm.conv1_fwd(x, w, impl='toeplitz')
+    ref = torch.nn.functional.conv3d(x.unsqueeze(1), w, padding=1)
+    assert _rel(y, _ndhwc(ref)) < 5e-3
+    yb = y.float().reshape(-1, 16)
+    assert torch.allclose(stats[:16], yb.sum(0), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(stats[16:], (yb * yb).sum(0), rtol=1e-3, atol=1e-2)
+    y16, _ = vbm.conv1_fwd(x.bfloat16(), w, impl='toeplitz')          # bf16 volumes: same padded matrix, same result
+    assert torch.equal(y16, y)
