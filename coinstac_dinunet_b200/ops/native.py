@@ -51,6 +51,10 @@ class _Lib:
         d.coinn_conv1_padded_shape.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
         d.coinn_conv1_pad_input.argtypes = [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_conv1_fwd_toeplitz.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
+        d.coinn_conv1_pad_input_hd.argtypes = [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
+        d.coinn_conv1_fused_stats.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p]
+        d.coinn_conv1_fused_pool.argtypes = [C.c_void_p] * 8 + [C.c_int] * 4 + [C.c_void_p]
+        d.coinn_conv1_fused_bwd.argtypes = [C.c_void_p] * 9 + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_conv1_wgrad_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_conv3d_halo.argtypes = [C.c_void_p] * 3 + [C.c_int] * 8 + [C.c_void_p]
         d.coinn_conv3d_wgrad_halo.argtypes = [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]

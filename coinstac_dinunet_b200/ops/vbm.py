@@ -63,6 +63,67 @@ def conv1_pad_input(x):
     return xp
 
 
+def conv1_fused_enabled():
+    """First block without its full-resolution tensors (conv1_fused.cu): conv recomputed in the pool and backward
+    kernels instead of stored.  COINN_CONV1_FUSED=0 falls back to conv1_fwd / bn_relu_pool_* / conv1_wgrad."""
+    return _os.environ.get('COINN_CONV1_FUSED', '1') != '0' and not _os.environ.get('COINN_CONV1_IMPL')
+
+
+def conv1_pad_input_hd(x):
+    """[N,D,H,W] fp32/bf16 -> zero-padded bf16 row matrix [N*(H+2)*(D+2), Wq], d' fastest (conv1_fused.cu)."""
+    N, D, H, W = x.shape
+    x = x.contiguous() if x.dtype in (BF16, _torch.float32) else x.float().contiguous()
+    rows, cols = _C.c_longlong(0), _C.c_int(0)
+    _nat.lib().coinn_conv1_padded_shape(N, D, H, W, _C.byref(rows), _C.byref(cols))
+    xp = _torch.empty((rows.value, cols.value), dtype=BF16, device=x.device)
+    _chk(_nat.lib().coinn_conv1_pad_input_hd(x.data_ptr(), 1 if x.dtype == BF16 else 0, xp.data_ptr(), N, D, H, W, _sp(x)),
+         'coinn_conv1_pad_input_hd')
+    _bump()
+    return xp
+
+
+def _w27(weight):
+    return weight.detach().float().reshape(16, 27).contiguous()
+
+
+def conv1_fused_stats(xp, weight, shape):
+    """-> stats[32]: per-channel sum and sum of squares of conv1(x) over the whole batch (nothing else is written)."""
+    N, D, H, W = shape
+    stats = _torch.zeros(32, dtype=_torch.float32, device=xp.device)
+    _chk(_nat.lib().coinn_conv1_fused_stats(xp.data_ptr(), _w27(weight).data_ptr(), stats.data_ptr(), N, D, H, W, _sp(xp)),
+         'coinn_conv1_fused_stats')
+    _bump()
+    return stats
+
+
+def conv1_fused_pool(xp, weight, mean, invstd, gamma, beta, shape):
+    """-> (p [N,D/2,H/2,W/2,16] bf16 = maxpool2(relu(bn(conv1(x)))), code uint8 like p: arg-max position | 8*active)."""
+    N, D, H, W = shape
+    p = _torch.empty((N, D // 2, H // 2, W // 2, 16), dtype=BF16, device=xp.device)
+    code = _torch.empty(p.shape, dtype=_torch.uint8, device=xp.device)
+    _chk(_nat.lib().coinn_conv1_fused_pool(xp.data_ptr(), _w27(weight).data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                           gamma.data_ptr(), beta.data_ptr(), p.data_ptr(), code.data_ptr(), N, D, H, W, _sp(xp)),
+         'coinn_conv1_fused_pool')
+    _bump()
+    return p, code
+
+
+def conv1_fused_bwd(xp, weight, mean, invstd, gamma, beta, p, code, dp, shape):
+    """-> (dW1 [16,1,3,3,3] fp32, dgamma, dbeta): BN/ReLU/pool backward + weight gradient with the conv output
+    recomputed on the tensor cores and its gradient kept in shared memory (never in HBM)."""
+    N, D, H, W = shape
+    dp = dp.contiguous()
+    acc = _torch.zeros(32, dtype=_torch.float32, device=xp.device)
+    _chk(_nat.lib().coinn_bn_pool_bwd_stats_pooled(p.data_ptr(), dp.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                                   acc.data_ptr(), p.numel() // 16, 16, _sp(xp)), 'bn_pool_bwd_stats_pooled')
+    dw = _torch.zeros(16 * 27, dtype=_torch.float32, device=xp.device)
+    _chk(_nat.lib().coinn_conv1_fused_bwd(xp.data_ptr(), _w27(weight).data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                          gamma.data_ptr(), acc.data_ptr(), dp.data_ptr(), code.data_ptr(), dw.data_ptr(),
+                                          N, D, H, W, _sp(xp)), 'coinn_conv1_fused_bwd')
+    _bump(2)
+    return dw.view(16, 1, 3, 3, 3), acc[16:], acc[:16]
+
+
 def conv1_fwd(x, weight, impl=None, xp=None):
     """x: [N,D,H,W] fp32/bf16 (single channel), weight: [16,1,3,3,3] -> (y [N,D,H,W,16] bf16, stats[32])."""
     N, D, H, W = x.shape
@@ -200,13 +261,26 @@ class ConvBnReluPoolFn(_torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, conv_w, gamma, beta, running_mean, running_var, eps, momentum, training, backend):
         first = x.dim() == 4
+        g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        if first and conv1_fused_enabled():
+            shape = tuple(x.shape)
+            xp = conv1_pad_input_hd(x)
+            if training:
+                stats = conv1_fused_stats(xp, conv_w, shape)
+                mean, invstd = bn_finalize(stats, x.numel(), eps, momentum, running_mean, running_var)
+            else:
+                mean, invstd = running_mean.float(), (running_var.float() + eps).rsqrt()
+            p, code = conv1_fused_pool(xp, conv_w, mean, invstd, g, b, shape)
+            ctx.save_for_backward(xp, conv_w, code, mean, invstd, g, b, p)
+            ctx.first, ctx.backend, ctx.training, ctx.fused_shape = first, backend, training, shape
+            return p
+        ctx.fused_shape = None
         if first:
             y, stats = conv1_fwd(x, conv_w)
         else:
             y = conv3d_fwd(x, conv_w, backend)
             stats = None
         N, D, H, W, C = y.shape
-        g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
         if training:
             if stats is None:
                 stats = bn_stats(y)
@@ -221,10 +295,14 @@ class ConvBnReluPoolFn(_torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dp):
-        x, conv_w, y, mean, invstd, g, b, p = ctx.saved_tensors
-        dy, dgamma, dbeta = bn_relu_pool_bwd(y, dp.contiguous(), mean, invstd, g, b, p=p)
         if not ctx.training:   # eval-mode BN has no batch-statistics terms; not a training path
             raise RuntimeError('ConvBnReluPoolFn.backward is only defined for training-mode BatchNorm')
+        if ctx.fused_shape is not None:
+            xp, conv_w, code, mean, invstd, g, b, p = ctx.saved_tensors
+            dw, dgamma, dbeta = conv1_fused_bwd(xp, conv_w, mean, invstd, g, b, p, code, dp, ctx.fused_shape)
+            return None, dw.to(conv_w.dtype), dgamma.to(g.dtype), dbeta.to(b.dtype), None, None, None, None, None, None
+        x, conv_w, y, mean, invstd, g, b, p = ctx.saved_tensors
+        dy, dgamma, dbeta = bn_relu_pool_bwd(y, dp.contiguous(), mean, invstd, g, b, p=p)
         if ctx.first:
             dx, dw = None, conv1_wgrad(dy, x)
         else:

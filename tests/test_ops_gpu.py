@@ -432,3 +432,78 @@ def test_conv1_toeplitz_fwd(dev, shape):
     assert torch.allclose(stats[16:], (yb * yb).sum(0), rtol=1e-3, atol=1e-2)
     y16, _ = vbm.conv1_fwd(x.bfloat16(), w, impl='toeplitz')          # bf16 volumes: same padded matrix, same result
     assert torch.equal(y16, y)
+
+
+def _conv1_block_reference(x, w, gamma, beta, dp=None, eps=1e-5):
+    """fp32 torch oracle of the first VBM block on bf16-rounded conv operands (training-mode BatchNorm)."""
+    w = w.clone().requires_grad_(True)
+    gamma, beta = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = torch.nn.functional.conv3d(x.unsqueeze(1), w, padding=1)
+    mean, var = y.mean((0, 2, 3, 4)), y.var((0, 2, 3, 4), unbiased=False)
+    z = (y - mean[None, :, None, None, None]) * (var + eps).rsqrt()[None, :, None, None, None]
+    z = torch.relu(z * gamma[None, :, None, None, None] + beta[None, :, None, None, None])
+    p = torch.nn.functional.max_pool3d(z, 2)
+    out = {'y': y.detach(), 'mean': mean.detach(), 'invstd': (var + eps).rsqrt().detach(), 'z': z.detach(), 'p': p.detach()}
+    if dp is not None:
+        p.backward(dp)
+        out.update(dw=w.grad, dgamma=gamma.grad, dbeta=beta.grad)
+    return out
+
+
+C1F_SHAPES = [(2, 9, 11, 13), (1, 6, 8, 70), (1, 131, 4, 10), (2, 4, 5, 121)]
+
+
+@pytest.mark.parametrize('shape', C1F_SHAPES)
+def test_conv1_fused_stats_and_pool(dev, shape):
+    """conv1_fused.cu STATS / POOL modes (conv recomputed, y never stored) vs the fp32 oracle."""
+    from coinstac_dinunet_b200.ops import vbm
+    torch.manual_seed(5)
+    N, D, H, W = shape
+    x = torch.randn(N, D, H, W, device=dev).bfloat16().float()
+    w = (torch.randn(16, 1, 3, 3, 3, device=dev) * 0.2).bfloat16().float()
+    gamma, beta = torch.rand(16, device=dev) + 0.5, torch.randn(16, device=dev) * 0.2
+    ref = _conv1_block_reference(x, w, gamma, beta)
+    xp = vbm.conv1_pad_input_hd(x)
+    rows = xp.view(N, H + 2, D + 2, -1)
+    assert torch.equal(rows[:, 1:-1, 1:-1, 1:W + 1].float(), x.permute(0, 2, 1, 3))
+    assert float(rows[:, 0].abs().max()) == 0 and float(rows[..., 0].abs().max()) == 0 and float(rows[..., W + 1:].abs().max()) == 0
+    stats = vbm.conv1_fused_stats(xp, w, shape)
+    yf = ref['y'].permute(0, 2, 3, 4, 1).reshape(-1, 16)
+    assert torch.allclose(stats[:16], yf.sum(0), rtol=1e-3, atol=5e-2)
+    assert torch.allclose(stats[16:], (yf * yf).sum(0), rtol=1e-3, atol=5e-2)
+    p, code = vbm.conv1_fused_pool(xp, w, ref['mean'], ref['invstd'], gamma, beta, shape)
+    p_ref = ref['p'].permute(0, 2, 3, 4, 1)
+    assert p.shape == p_ref.shape and code.shape == p.shape
+    assert float((p.float() - p_ref).abs().max()) < 0.03 + 0.01 * float(p_ref.abs().max())
+    # the code byte must point at a window element that attains the maximum, and flag ReLU activity
+    PD, PH, PW = D // 2, H // 2, W // 2
+    zw = ref['z'][:, :, :2 * PD, :2 * PH, :2 * PW].reshape(N, 16, PD, 2, PH, 2, PW, 2).permute(0, 2, 4, 6, 1, 3, 5, 7)
+    zw = zw.reshape(N, PD, PH, PW, 16, 8)
+    picked = zw.gather(-1, (code & 7).long().unsqueeze(-1)).squeeze(-1)
+    assert float((picked - p_ref).abs().max()) < 2e-3
+    active = (code >> 3) == 1
+    assert bool(((p_ref > 1e-3) <= active).all()) and bool((active <= (p_ref > -1e-3)).all())
+
+
+@pytest.mark.parametrize('shape', C1F_SHAPES)
+def test_conv1_fused_block_backward(dev, shape):
+    """conv1_fused.cu BWD mode: recomputed conv -> BN/ReLU/pool backward in registers -> dy in shared memory ->
+    tcgen05 weight-gradient GEMM, vs autograd through the fp32 torch block."""
+    from coinstac_dinunet_b200.ops import vbm
+    torch.manual_seed(6)
+    N, D, H, W = shape
+    x = torch.randn(N, D, H, W, device=dev).bfloat16().float()
+    w = (torch.randn(16, 1, 3, 3, 3, device=dev) * 0.2).bfloat16().float()
+    gamma, beta = torch.rand(16, device=dev) + 0.5, torch.randn(16, device=dev) * 0.2
+    dp = torch.randn(N, 16, D // 2, H // 2, W // 2, device=dev).bfloat16().float()
+    ref = _conv1_block_reference(x, w, gamma, beta, dp=dp)
+    rm, rv = torch.zeros(16, device=dev), torch.ones(16, device=dev)
+    xin = x.clone().requires_grad_(False)
+    wq, gq, bq = w.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    p = vbm.ConvBnReluPoolFn.apply(xin, wq, gq, bq, rm, rv, 1e-5, 0.1, True, 'auto')
+    assert float((p.float() - ref['p'].permute(0, 2, 3, 4, 1)).abs().max()) < 0.03 + 0.01 * float(ref['p'].abs().max())
+    p.backward(dp.permute(0, 2, 3, 4, 1).contiguous().to(p.dtype))
+    cos = torch.nn.functional.cosine_similarity(wq.grad.flatten(), ref['dw'].flatten(), dim=0)
+    assert float(cos) > 0.999 and _rel(wq.grad, ref['dw']) < 3e-2, (float(cos), _rel(wq.grad, ref['dw']))
+    assert _rel(gq.grad, ref['dgamma']) < 3e-2 and _rel(bq.grad, ref['dbeta']) < 3e-2
+    assert torch.allclose(rm, 0.1 * ref['mean'], rtol=1e-3, atol=1e-4)
