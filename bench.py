@@ -244,9 +244,31 @@ def run_ours(a):
                        'l2_policy': 'inputs rotate over 4 distinct batches; activations per step >> 126 MB L2'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     dist.barrier(device_ids=[local])
     dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------ stdout
+_JSON_FD = None
+
+
+def _guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the
+    first communicator), so everything that is not the result goes to stderr: fd 1 is pointed at fd 2 for the run
+    and the JSON line is written to the saved descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 # -------------------------------------------------------------------------------- reference
@@ -256,7 +278,7 @@ def run_reference(a):
         import ref_runner
         ref_runner.import_reference()
     except Exception as exc:  # noqa: BLE001
-        print(json.dumps({'impl': 'reference', 'unavailable': f'{type(exc).__name__}: {exc}'[:300]}))
+        emit({'impl': 'reference', 'unavailable': f'{type(exc).__name__}: {exc}'[:300]})
         return
     import torch
     import torch.distributed as dist
@@ -283,7 +305,7 @@ def run_reference(a):
         value = a.gpus * batch * a.steps / (ms / 1e3)
         h2d = batch * (int(torch.tensor(shape).prod()) * 4 + 8)
         nparam = sum(p.numel() for p in eng.cache['nn']['model'].parameters())
-        print(json.dumps({
+        emit({
             'metric': 'samples/sec (whole box, max over sites) VBM-3D-CNN dSGD' if a.model == 'vbm'
             else 'samples/sec (whole box, max over sites) FreeSurfer-MLP dSGD',
             'value': value, 'unit': 'samples/s', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
@@ -297,12 +319,13 @@ def run_reference(a):
             'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d + nparam * 4,
                     'd2h_bytes_per_step': nparam * 4 + 4,
                     'note': 'the reference has no device-only mode: every step is host<->device + files'},
-            'gpu_launches': 0}), flush=True)
+            'gpu_launches': 0})
     dist.barrier(device_ids=[local])
     dist.destroy_process_group()
 
 
 if __name__ == '__main__':
+    _guard_stdout()
     args = parse()
     if args.impl == 'reference':
         run_reference(args)

@@ -23,6 +23,7 @@
 //
 //   dW~[kh][(wl, c), kd*16 + k] += sum_rows dy[row, (wl, c)] * XP2[line h+kh, row + kd, 8j + k],   dW1[c,kd,kh,kw] = sum_wl dW~[kh][(wl,c), kd*16 + wl + kw]
 #include "umma.cuh"
+#include <cstdlib>
 
 namespace coinn {
 
@@ -30,8 +31,10 @@ enum { C1F_STATS = 0, C1F_POOL = 1, C1F_BWD = 2 };
 
 constexpr int C1F_THREADS = 320;                       // warp 0: TMA, warp 1: MMA, warps 2-9: two epilogue groups
 constexpr int C1F_ROWS = 136;                          // 128 + 2 halo rows, rounded up to 8
-constexpr uint32_t C1F_SLAB = C1F_ROWS * 32;           // one window: [136 rows][16 bf16]
+constexpr uint32_t C1F_SLAB = C1F_ROWS * 32;           // BWD: one window [136 rows][16 w'] per output block (32B swizzle)
 constexpr uint32_t C1F_STAGE = 4 * C1F_SLAB;           // input lines h' .. h'+3 of one output block (17 KB)
+constexpr uint32_t C1F_WSLAB = C1F_ROWS * 128;         // STATS / POOL: one window [136 rows][64 w'] serves 7 output blocks (128B swizzle)
+constexpr uint32_t C1F_WSTAGE = 4 * C1F_WSLAB;         // 68 KB
 constexpr uint32_t C1F_T_BYTES = 9 * 4096;             // Toeplitz matrices T_{kd,kh}: [2 k-chunks][128 n][8 k] bf16
 constexpr uint32_t C1F_DY_BYTES = 32768;               // dy tile: 2 M-blocks x [128 rows][128 B], 128B swizzle
 constexpr int C1F_MAX_STAGES = 8;
@@ -40,7 +43,7 @@ struct C1FParams {
     const float* w;             // [16][27] fp32
     int N, D, H, W;
     int Dp, Hp;                 // D + 2, H + 2
-    int nblk, groups;           // ceil(W / 8) output blocks per line, groups of 8 blocks
+    int nblk, groups, bpg;      // ceil(W / 8) output blocks per line; groups of bpg blocks (8, or 7 per 64-column window)
     int tpl, hpairs;            // 128-row tiles per d-line, ceil(H / 2)
     int num_units;              // N * hpairs * tpl * groups
     int stages;
@@ -55,6 +58,7 @@ struct C1FParams {
     const float* acc;           // BWD: [32] sum(g), sum(g * xhat) over the batch (bn_pool_bwd_stats_pooled)
     float inv_count;            // BWD: 1 / (N*D*H*W)
     float* dw;                  // BWD: [16][27] fp32 (zeroed)
+    int dbg;                    // COINN_C1F_DEBUG (profiling only): 1 = STATS epilogue skips the math, 2 = also the TMEM loads
 };
 
 // xp2[(n*Hp + h')*Dp + d'][w'] = x[n, d'-1, h'-1, w'-1] (zero outside); one thread per 16-byte chunk
@@ -103,13 +107,19 @@ template <int MODE>
 __global__ void __launch_bounds__(C1F_THREADS, 1)
 conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams p) {
     constexpr int NBUF = MODE == C1F_BWD ? 2 : 4;            // conv accumulators (128 TMEM columns each)
+    // TMA moves ~one box row per 3-4 cycles whatever its width, and 32-byte rows made the recompute kernels TMA-bound
+    // (ncu: tensor pipe 45 % active, epilogue warps starved).  STATS / POOL therefore load 128-byte rows: a window of
+    // 64 input columns is the operand of 7 output blocks, block m starting 16*m bytes into the swizzled row.
+    constexpr bool WIDE = MODE != C1F_BWD;
+    constexpr uint32_t SLAB = WIDE ? C1F_WSLAB : C1F_SLAB;
+    constexpr uint32_t STAGE = 4 * SLAB;
     constexpr uint32_t WG_COL = 256;                         // BWD: weight-gradient accumulators (48 columns) at columns 256 + kh*64
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* t_smem = smem;
     uint8_t* stage_base = smem + C1F_T_BYTES;
-    uint8_t* dy_smem = stage_base + (size_t)p.stages * C1F_STAGE;            // BWD only: 2 x 32 KB
+    uint8_t* dy_smem = stage_base + (size_t)p.stages * STAGE;            // BWD only: 2 x 32 KB
     uint64_t* bars = reinterpret_cast<uint64_t*>(dy_smem + (MODE == C1F_BWD ? 2 * C1F_DY_BYTES : 0));
     uint64_t* full_bar = bars;                               // [stages] TMA -> MMA
     uint64_t* empty_bar = bars + C1F_MAX_STAGES;             // [stages] MMA -> TMA
@@ -149,30 +159,40 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams 
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();                               // uniform loop, one issuing lane (see the MMA warp)
             uint32_t it = 0;
             for (int u = first; u < p.num_units; u += step) {
                 int n, hp, t, g;
                 c1f_unit(p, u, n, hp, t, g);
-                const int nb = (p.nblk - g * 8) < 8 ? (p.nblk - g * 8) : 8;
+                const int nb = (p.nblk - g * p.bpg) < p.bpg ? (p.nblk - g * p.bpg) : p.bpg;
                 const int row0 = (n * p.Hp + 2 * hp) * p.Dp + t * 128;
-                for (int jj = 0; jj < nb; ++jj, ++it) {
+                const int nloads = WIDE ? 1 : nb;                          // one window per unit / per output block
+                for (int jj = 0; jj < nloads; ++jj, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-                    uint8_t* dst = stage_base + (size_t)s * C1F_STAGE;
-                    mbar_arrive_expect_tx(&full_bar[s], C1F_STAGE);
+                    uint8_t* dst = stage_base + (size_t)s * STAGE;
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], STAGE);
 #pragma unroll
                     for (int l = 0; l < 4; ++l)
-                        tma_load_2d(dst + l * C1F_SLAB, &tmap_xp, &full_bar[s], (g * 8 + jj) * 8, row0 + l * p.Dp);
+                        if (leader) tma_load_2d(dst + l * SLAB, &tmap_xp, &full_bar[s], (g * p.bpg + jj) * 8, row0 + l * p.Dp);
                 }
             }
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(128, 128, 1, 0, 0);
+        // The WHOLE warp runs this loop and one elected lane issues.  With the loop under `if (lane == 0)` ptxas cannot
+        // prove that the descriptors are warp-uniform and wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST
+        // "waterfall" (7 dependent R2UR per MMA): ~150 cycles of issue latency per MMA against a 64-cycle tensor floor,
+        // i.e. the tensor pipe sat idle 55 % of the time (profiles/ncu_conv1_fused_v1.txt).  Uniform control flow lets
+        // the descriptor arithmetic live in uniform registers.
+        {
+            const bool leader = elect_one();
+            const uint32_t idesc = make_idesc_f16(128, p.dbg == 3 ? 64 : 128, 1, 0, 0);      // dbg 3: half-width MMAs (timing experiment)
+            const uint32_t kd_rows = p.dbg == 5 ? 0u : (WIDE ? 8u : 2u);                     // dbg 5: no row shift (timing experiment)
             constexpr uint32_t idesc_w = make_idesc_f16(128, 48, 1, 1, 1);
-            const uint64_t a_const = make_smem_desc(0, 16, 256, SMEM_LAYOUT_SW32);         // K-major, 32-byte rows
+            const uint64_t a_const = WIDE ? make_smem_desc(0, 16, 1024, SMEM_LAYOUT_SW128)  // K-major, 128-byte rows
+                                          : make_smem_desc(0, 16, 256, SMEM_LAYOUT_SW32);   // K-major, 32-byte rows
             const uint64_t b_const = make_smem_desc(0, 2048, 128, SMEM_LAYOUT_NONE);
             const uint64_t wa_const = make_smem_desc(0, 16384, 1024, SMEM_LAYOUT_SW128);   // dy: MN-major, 2 blocks of 64
             const uint64_t wb_const = make_smem_desc(0, 32, 256, SMEM_LAYOUT_SW32);        // window: MN-major, block = row shift
@@ -189,46 +209,48 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams 
                 for (int k = 0; k < 8; ++k) {
 #pragma unroll
                     for (int kh = 0; kh < 3; ++kh)
-                        umma_f16(tmem_base + WG_COL + kh * 64, wa_const | (a0 + k * 128), wb_const | (prev_slab16 + kh * (C1F_SLAB / 16) + k * 32),
+                        if (leader) umma_f16(tmem_base + WG_COL + kh * 64, wa_const | (a0 + k * 128), wb_const | (prev_slab16 + kh * (C1F_SLAB / 16) + k * 32),
                                  idesc_w, (h | (uint32_t)k) ? 1u : 0u);
                 }
-                umma_commit(&dy_free[bb]);
-                if (prev_ab) umma_commit(&empty_bar[prev_stage]);
+                if (leader) { umma_commit(&dy_free[bb]); if (prev_ab) umma_commit(&empty_bar[prev_stage]); }
+                __syncwarp();
             };
             for (int u = first; u < p.num_units; u += step) {
                 int n, hp, t, g;
                 c1f_unit(p, u, n, hp, t, g);
-                const int nb = (p.nblk - g * 8) < 8 ? (p.nblk - g * 8) : 8;
-                for (int jj = 0; jj < nb; ++jj, ++it) {
+                const int nb = (p.nblk - g * p.bpg) < p.bpg ? (p.nblk - g * p.bpg) : p.bpg;
+                for (int jj = 0; jj < nb; ++jj) {
                     const uint32_t s = it % STAGES;
-                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
-                    const uint32_t st16 = (smem_u32(stage_base + (size_t)s * C1F_STAGE) & 0x3FFFFu) >> 4;
+                    if (!WIDE || jj == 0) mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    const uint32_t st16 = (smem_u32(stage_base + (size_t)s * STAGE) & 0x3FFFFu) >> 4;
 #pragma unroll
                     for (int ab = 0; ab < 2; ++ab, ++hb) {
                         const uint32_t b = hb & (NBUF - 1);
                         mbar_wait(&tmem_empty[b], ((hb / NBUF) & 1) ^ 1);
                         tcgen05_after_sync();
                         const uint32_t d_tmem = tmem_base + b * 128;
-                        const uint32_t a0 = st16 + ab * (C1F_SLAB / 16);
+                        const uint32_t a0 = st16 + ab * (SLAB / 16) + (WIDE ? (uint32_t)jj : 0u);   // block jj: +16 bytes per block
 #pragma unroll
                         for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
                             for (int kh = 0; kh < 3; ++kh)
-                                umma_f16(d_tmem, a_const | (a0 + kh * (C1F_SLAB / 16) + kd * 2), b_const | (t16 + (kd * 3 + kh) * 256), idesc,
+                                if (leader) umma_f16(d_tmem, a_const | (a0 + kh * (SLAB / 16) + kd * kd_rows), b_const | (t16 + (kd * 3 + kh) * 256), idesc,
                                          (kd | kh) ? 1u : 0u);
                         }
-                        umma_commit(&tmem_full[b]);
+                        if (leader) umma_commit(&tmem_full[b]);
+                        __syncwarp();
                         if (MODE == C1F_BWD) {
                             if (hb > 0) issue_wgrad(hb - 1);
                             prev_slab16 = a0; prev_stage = s; prev_ab = ab;
                         }
                     }
-                    if (MODE != C1F_BWD) umma_commit(&empty_bar[s]);
+                    if (WIDE ? (jj == nb - 1) : false) { if (leader) umma_commit(&empty_bar[s]); ++it; }
+                    if (!WIDE) ++it;
                 }
             }
             if (MODE == C1F_BWD) {
                 if (hb > 0) issue_wgrad(hb - 1);
-                umma_commit(done_bar);
+                if (leader) umma_commit(done_bar);
             }
         }
     } else {
@@ -246,11 +268,11 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams 
             for (int u = first; u < p.num_units; u += step) {
                 int n, hp, t, g;
                 c1f_unit(p, u, n, hp, t, g);
-                const int nb = (p.nblk - g * 8) < 8 ? (p.nblk - g * 8) : 8;
+                const int nb = (p.nblk - g * p.bpg) < p.bpg ? (p.nblk - g * p.bpg) : p.bpg;
                 const bool row_ok = t * 128 + r < p.D;
                 for (int jj = 0; jj < nb; ++jj, ++blk) {
                     if ((blk & 1u) != (uint32_t)grp) continue;
-                    const int w0 = (g * 8 + jj) * 8;
+                    const int w0 = (g * p.bpg + jj) * 8;
 #pragma unroll
                     for (int ab = 0; ab < 2; ++ab) {
                         const uint32_t b = 2 * (blk & 1) + ab;
@@ -259,13 +281,14 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams 
                         const bool line_ok = row_ok && (2 * hp + ab) < p.H;
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
+                            if (p.dbg >= 2) break;
                             uint32_t v[4][16];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) tmem_ld_32x32b_x16(tmem_base + lane_off + b * 128 + (half * 4 + i) * 16, v[i]);
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                if (line_ok && w0 + half * 4 + i < p.W) {
+                                if (line_ok && w0 + half * 4 + i < p.W && (p.dbg == 0 || v[i][0] == 0x7fc01234u)) {
 #pragma unroll
                                     for (int c = 0; c < 16; ++c) {
                                         const float f = __uint_as_float(v[i][c]);
@@ -290,17 +313,18 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams 
 #pragma unroll
             for (int c = 0; c < 16; ++c) { sc[c] = p.gamma[c] * p.invstd[c]; sh[c] = p.beta[c] - p.mean[c] * sc[c]; }
             const bool odd = lane & 1;
+            const uint32_t dbit = odd ? 4u : 0u;
             uint32_t blk = 0;
             for (int u = first; u < p.num_units; u += step) {
                 int n, hp, t, g;
                 c1f_unit(p, u, n, hp, t, g);
-                const int nb = (p.nblk - g * 8) < 8 ? (p.nblk - g * 8) : 8;
+                const int nb = (p.nblk - g * p.bpg) < p.bpg ? (p.nblk - g * p.bpg) : p.bpg;
                 const int pd = (t * 128 + r) >> 1;
                 const bool cell_row_ok = pd < PD && hp < PH;
                 const long long cell_row = (((long long)n * PD + pd) * PH + hp) * PW;
                 for (int jj = 0; jj < nb; ++jj, ++blk) {
                     if ((blk & 1u) != (uint32_t)grp) continue;
-                    const int w0 = (g * 8 + jj) * 8;
+                    const int w0 = (g * p.bpg + jj) * 8;
                     const uint32_t bA = 2 * (blk & 1), bB = bA + 1;
                     mbar_wait(&tmem_full[bA], (blk >> 1) & 1);
                     mbar_wait(&tmem_full[bB], (blk >> 1) & 1);
@@ -313,32 +337,33 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams 
                         tmem_ld_32x32b_x16(tmem_base + lane_off + bB * 128 + (2 * i) * 16, v[2]);
                         tmem_ld_32x32b_x16(tmem_base + lane_off + bB * 128 + (2 * i + 1) * 16, v[3]);
                         tmem_ld_wait();
-                        uint32_t pk[4] = {0u, 0u, 0u, 0u};                  // this lane's 8 channels, bf16
-                        uint32_t ck[2] = {0u, 0u};                          // ... and their code bytes
+                        // The window position (3 bits) rides in the low mantissa bits of the candidate, so the whole
+                        // 2x2x2 arg-max is FMNMX on single registers (7 fp32 ulps of noise, far below the bf16 output;
+                        // exact ties go to the larger position instead of the smaller one).
+                        float m[16];
 #pragma unroll
                         for (int c = 0; c < 16; ++c) {
-                            float m = fmaf(__uint_as_float(v[0][c]), sc[c], sh[c]);
-                            uint32_t k = 0;
+                            float e[4];
 #pragma unroll
-                            for (int j = 1; j < 4; ++j) {
+                            for (int j = 0; j < 4; ++j) {
                                 const float z = fmaf(__uint_as_float(v[j][c]), sc[c], sh[c]);
-                                if (z > m) { m = z; k = j; }
+                                e[j] = __uint_as_float((__float_as_uint(z) & ~7u) | (dbit | (uint32_t)j));
                             }
-                            const float om = __shfl_xor_sync(0xffffffffu, m, 1);
-                            const uint32_t ok = __shfl_xor_sync(0xffffffffu, k, 1);
-                            // window scan order is (d, h, w): the even lane (d even) keeps ties
-                            const bool take_other = odd ? !(m > om) : (om > m);
-                            float fm = take_other ? om : m;
-                            uint32_t fk = (take_other ? ok : k) | ((take_other != odd) ? 4u : 0u);
-                            const bool active = fm > 0.f;
-                            fm = active ? fm : 0.f;
-                            fk |= active ? 8u : 0u;
-                            if ((c >> 3) == (odd ? 1 : 0)) {                 // even lane stores channels 0-7, odd lane 8-15
-                                const int cc = c & 7;
-                                const uint32_t hbits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(fm));
-                                pk[cc >> 1] |= hbits << (16 * (cc & 1));
-                                ck[cc >> 2] |= fk << (8 * (cc & 3));
-                            }
+                            m[c] = fmaxf(fmaxf(e[0], e[1]), fmaxf(e[2], e[3]));
+                        }
+                        uint32_t pk[4] = {0u, 0u, 0u, 0u};                  // this lane's 8 channels (even lane 0-7, odd lane 8-15), bf16
+                        uint32_t ck[2] = {0u, 0u};                          // ... and their code bytes
+#pragma unroll
+                        for (int cc = 0; cc < 8; ++cc) {
+                            const float send = odd ? m[cc] : m[cc + 8];     // the partner lane (d ^ 1) finalises the other 8 channels
+                            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                            const float best = fmaxf(odd ? m[cc + 8] : m[cc], recv);
+                            const uint32_t bits = __float_as_uint(best);
+                            const float val = __uint_as_float(bits & ~7u);
+                            const bool active = val > 0.f;
+                            const uint32_t hbits = active ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16(val)) : 0u;
+                            pk[cc >> 1] |= hbits << (16 * (cc & 1));
+                            ck[cc >> 2] |= ((bits & 7u) | (active ? 8u : 0u)) << (8 * (cc & 3));
                         }
                         const int pw = (w0 >> 1) + i;
                         if (cell_row_ok && pw < PW) {
@@ -354,21 +379,24 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams 
             }
         } else {
             // dy = sc * (g - c1 - xhat * c2) = S*g + (A + B*y)
-            float cS[16], cA[16], cB[16];
+            float cA[16], cB[16];
+            float* cS = red;                                               // S lives in shared memory (16 fewer live registers)
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 const float is = p.invstd[c];
-                cS[c] = p.gamma[c] * is;
-                cB[c] = -cS[c] * (p.acc[16 + c] * p.inv_count) * is;
-                cA[c] = -cS[c] * (p.acc[c] * p.inv_count) - cB[c] * p.mean[c];
+                const float S = p.gamma[c] * is;
+                cB[c] = -S * (p.acc[16 + c] * p.inv_count) * is;
+                cA[c] = -S * (p.acc[c] * p.inv_count) - cB[c] * p.mean[c];
+                if (ew == 0 && lane == 0) cS[c] = S;
             }
+            asm volatile("bar.sync 2, 256;" ::: "memory");               // the 8 epilogue warps
             const uint32_t dy_addr = smem_u32(dy_smem) + (uint32_t)grp * C1F_DY_BYTES + (uint32_t)r * 128u;
             const uint32_t sw = (uint32_t)(r & 7);
             uint32_t hb = 0;
             for (int u = first; u < p.num_units; u += step) {
                 int n, hp, t, g;
                 c1f_unit(p, u, n, hp, t, g);
-                const int nb = (p.nblk - g * 8) < 8 ? (p.nblk - g * 8) : 8;
+                const int nb = (p.nblk - g * p.bpg) < p.bpg ? (p.nblk - g * p.bpg) : p.bpg;
                 const int d = t * 128 + r, h = 2 * hp + grp;               // this group's line: A (grp 0) or B (grp 1)
                 const bool row_ok = d < p.D && h < p.H;
                 const bool cell_row_ok = row_ok && (d >> 1) < PD && (h >> 1) < PH;
@@ -377,7 +405,21 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams 
                 for (int jj = 0; jj < nb; ++jj, hb += 2) {
                     const uint32_t my = hb + (uint32_t)grp;                // half-block index handled by this group
                     const uint32_t b = (uint32_t)grp;
-                    const int w0 = (g * 8 + jj) * 8;
+                    const int w0 = (g * p.bpg + jj) * 8;
+                    // all global loads of this half-block (arg-max codes + pooled gradients of its 4 pool cells) are issued
+                    // before the barrier waits: their latency hides behind the MMAs instead of stalling every iteration
+                    uint4 cdv[4], g0v[4], g1v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int pw = (w0 >> 1) + i;
+                        cdv[i] = make_uint4(0u, 0u, 0u, 0u); g0v[i] = cdv[i]; g1v[i] = cdv[i];
+                        if (cell_row_ok && pw < PW) {
+                            const long long cell = cell_row + pw;
+                            cdv[i] = ld_global_nc_128(p.code + cell * 16);
+                            g0v[i] = ld_global_nc_128(p.dpool + cell * 16);
+                            g1v[i] = ld_global_nc_128(p.dpool + cell * 16 + 8);
+                        }
+                    }
                     mbar_wait(&tmem_full[b], (my >> 1) & 1);
                     mbar_wait(&dy_free[b], ((my >> 1) & 1) ^ 1);           // wgrad MMAs of the previous tile in this buffer are done
                     tcgen05_after_sync();
@@ -386,14 +428,7 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams 
                         uint32_t v[2][16];
                         tmem_ld_32x32b_x16(tmem_base + lane_off + b * 128 + (2 * i) * 16, v[0]);
                         tmem_ld_32x32b_x16(tmem_base + lane_off + b * 128 + (2 * i + 1) * 16, v[1]);
-                        const int pw = (w0 >> 1) + i;
-                        uint4 cd = make_uint4(0u, 0u, 0u, 0u), g0 = cd, g1 = cd;
-                        if (cell_row_ok && pw < PW) {
-                            const long long cell = cell_row + pw;
-                            cd = ld_global_nc_128(p.code + cell * 16);
-                            g0 = ld_global_nc_128(p.dpool + cell * 16);
-                            g1 = ld_global_nc_128(p.dpool + cell * 16 + 8);
-                        }
+                        const uint4 cd = cdv[i], g0 = g0v[i], g1 = g1v[i];
                         const uint32_t cdw[4] = {cd.x, cd.y, cd.z, cd.w};
                         const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
                         float gsc[16];
@@ -475,7 +510,7 @@ static inline void c1f_geometry(int N, int D, int H, int W, C1FParams& p, int& W
     p.N = N; p.D = D; p.H = H; p.W = W;
     p.Dp = D + 2; p.Hp = H + 2;
     p.nblk = (W + 7) / 8;
-    p.groups = (p.nblk + 7) / 8;
+    p.groups = (p.nblk + p.bpg - 1) / p.bpg;
     p.tpl = (D + 127) / 128;
     p.hpairs = (H + 1) / 2;
     p.num_units = N * p.hpairs * p.tpl * p.groups;
@@ -485,13 +520,19 @@ static inline void c1f_geometry(int N, int D, int H, int W, C1FParams& p, int& W
 template <int MODE>
 static int c1f_launch(const void* xp, C1FParams& p, int N, int D, int H, int W, cudaStream_t st) {
     int Wq;
+    constexpr bool WIDE = MODE != C1F_BWD;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("COINN_C1F_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+    p.bpg = WIDE ? 7 : 8;
     c1f_geometry(N, D, H, W, p, Wq);
     const long long rows = (long long)N * p.Hp * p.Dp;
     if (rows + 4LL * p.Dp + 512 >= (1LL << 31)) return -1;
-    p.stages = MODE == C1F_BWD ? 5 : 8;
-    const int smem_bytes = (int)C1F_T_BYTES + p.stages * (int)C1F_STAGE + (MODE == C1F_BWD ? 2 * (int)C1F_DY_BYTES : 0) + 1024 + 1024;
+    p.stages = WIDE ? 2 : 5;
+    const int smem_bytes = (int)C1F_T_BYTES + p.stages * (int)(WIDE ? C1F_WSTAGE : C1F_STAGE) + (WIDE ? 0 : 2 * (int)C1F_DY_BYTES) + 1024 + 1024;
     CUtensorMap tx;
-    if (make_tmap_2d_bf16(&tx, xp, (uint64_t)rows, (uint64_t)Wq, (uint64_t)Wq * 2, C1F_ROWS, 16, CU_TENSOR_MAP_SWIZZLE_32B) != 0) return -3;
+    if (make_tmap_2d_bf16(&tx, xp, (uint64_t)rows, (uint64_t)Wq, (uint64_t)Wq * 2, C1F_ROWS, WIDE ? 64 : 16,
+                          WIDE ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B) != 0) return -3;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv1_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

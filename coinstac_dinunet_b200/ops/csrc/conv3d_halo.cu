@@ -80,10 +80,11 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     const int first_tile = blockIdx.x, tile_step = gridDim.x;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();   // whole warp runs the loop (uniform descriptors), one lane issues
             // weights: one [COUT x 8] box per k-chunk, resident for the lifetime of the CTA
-            mbar_arrive_expect_tx(w_bar, KCH * W_CHUNK_BYTES);
-            for (int kc = 0; kc < KCH; ++kc) tma_load_2d(w_smem + kc * W_CHUNK_BYTES, &tmap_w, w_bar, kc * 8, 0);
+            if (leader) mbar_arrive_expect_tx(w_bar, KCH * W_CHUNK_BYTES);
+            for (int kc = 0; kc < KCH; ++kc) if (leader) tma_load_2d(w_smem + kc * W_CHUNK_BYTES, &tmap_w, w_bar, kc * 8, 0);
             uint32_t it = 0;
             for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++it) {
                 const int plane = tile / p.tiles_h, h0 = (tile % p.tiles_h) * p.TH;
@@ -91,21 +92,22 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 const int s = it % STAGES;
                 mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
                 uint8_t* dst = stage_base + (size_t)s * stage_bytes;
-                mbar_arrive_expect_tx(&full_bar[s], REGIONS * p.region_tx);
+                if (leader) mbar_arrive_expect_tx(&full_bar[s], REGIONS * p.region_tx);
 #pragma unroll
                 for (int kd = 0; kd < 3; ++kd) {
                     if (FULLPIX) {
-                        tma_load_5d_h(dst + kd * p.region_bytes, &tmap_x, &full_bar[s], 0, -1, h0 - 1, d + kd - 1, n);
+                        if (leader) tma_load_5d_h(dst + kd * p.region_bytes, &tmap_x, &full_bar[s], 0, -1, h0 - 1, d + kd - 1, n);
                     } else {
 #pragma unroll
                         for (int c = 0; c < CHUNKS; ++c)
-                            tma_load_5d_h(dst + (kd * CHUNKS + c) * p.region_bytes, &tmap_x, &full_bar[s], c * 8, -1, h0 - 1, d + kd - 1, n);
+                            if (leader) tma_load_5d_h(dst + (kd * CHUNKS + c) * p.region_bytes, &tmap_x, &full_bar[s], c * 8, -1, h0 - 1, d + kd - 1, n);
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();   // whole warp runs the loop (uniform descriptors), one lane issues
             constexpr uint32_t idesc = make_idesc_f16(128, COUT, 1, 0, 0);
             mbar_wait(w_bar, 0);
             const uint32_t w_addr = smem_u32(w_smem);
@@ -127,8 +129,9 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 const uint64_t a_const = FULLPIX ? make_smem_desc(0, 16, 8 * PIXB, A_LAYOUT)
                                                  : make_smem_desc(0, p.region_bytes, 128, SMEM_LAYOUT_NONE);
                 const uint64_t b_const = make_smem_desc(0, W_CHUNK_BYTES, 128, SMEM_LAYOUT_NONE);
-                uint32_t b16 = (w_addr & 0x3FFFFu) >> 4;
-                uint32_t accumulate = 0;
+                const uint32_t w16 = (w_addr & 0x3FFFFu) >> 4;
+                // every offset below is a compile-time multiple of a warp-uniform value: ptxas keeps both descriptors in
+                // uniform registers and the 27 * CIN/16 UTCHMMA issue back to back
 #pragma unroll
                 for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
@@ -140,15 +143,14 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                                 const uint32_t a16 = FULLPIX
                                     ? halo16 + kd * region16 + kh * row16 + kw * (PIXB / 16) + j * 2
                                     : halo16 + (kd * CHUNKS + 2 * j) * region16 + kh * row16 + kw;
-                                umma_f16(d_tmem, a_const | a16, b_const | b16, idesc, accumulate);
-                                accumulate = 1;
-                                b16 += 2 * (W_CHUNK_BYTES / 16);
+                                const uint32_t b16 = w16 + (uint32_t)(((kd * 3 + kh) * 3 + kw) * (CIN / 16) + j) * (2 * (W_CHUNK_BYTES / 16));
+                                if (leader) umma_f16(d_tmem, a_const | a16, b_const | b16, idesc, (kd | kh | kw | j) ? 1u : 0u);
                             }
                         }
                     }
                 }
-                umma_commit(&empty_bar[s]);
-                umma_commit(&tmem_full[a]);
+                if (leader) umma_commit(&empty_bar[s]);
+                if (leader) umma_commit(&tmem_full[a]);
             }
         }
     } else {

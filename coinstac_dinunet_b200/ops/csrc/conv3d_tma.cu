@@ -83,7 +83,8 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int tiles_per_slice = p.tiles_w * p.tiles_h;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();   // whole warp runs the loop (uniform descriptors), one lane issues
             uint32_t it = 0;
             for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
                 const int slice = tile / tiles_per_slice, rem = tile % tiles_per_slice;
@@ -96,15 +97,16 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                         const int s = it % STAGES;
                         mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
                         uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES_RAW);
-                        tma_load_5d(a_dst, &tmap_x, &full_bar[s], b * CB, w0 + kw - 1, h0 + kh - 1, d + kd - 1, n);
-                        tma_load_2d(a_dst + Cfg::A_BYTES, &tmap_w, &full_bar[s], tap * CIN + b * CB, 0);
+                        if (leader) mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES_RAW);
+                        if (leader) tma_load_5d(a_dst, &tmap_x, &full_bar[s], b * CB, w0 + kw - 1, h0 + kh - 1, d + kd - 1, n);
+                        if (leader) tma_load_2d(a_dst + Cfg::A_BYTES, &tmap_w, &full_bar[s], tap * CIN + b * CB, 0);
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();   // whole warp runs the loop (uniform descriptors), one lane issues
             constexpr uint32_t idesc = make_idesc_f16(128, COUT, 1, 0, 0);
             uint32_t it = 0, t = 0;
             for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++t) {
@@ -120,13 +122,13 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
                     for (int k = 0; k < CB / 16; ++k) {
-                        umma_f16(d_tmem, make_smem_desc(a_addr + k * 32, 16, Cfg::SBO, Cfg::LAYOUT),
+                        if (leader) umma_f16(d_tmem, make_smem_desc(a_addr + k * 32, 16, Cfg::SBO, Cfg::LAYOUT),
                                  make_smem_desc(b_addr + k * 32, 16, Cfg::SBO, Cfg::LAYOUT), idesc,
                                  (u > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[s]);
+                    if (leader) umma_commit(&empty_bar[s]);
                 }
-                umma_commit(&tmem_full[a]);
+                if (leader) umma_commit(&tmem_full[a]);
             }
         }
     } else {

@@ -80,7 +80,8 @@ conv3d_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     const int my_tiles = first < p.num_tiles ? (p.num_tiles - first + step - 1) / step : 0;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();   // whole warp runs the loop (uniform descriptors), one lane issues
             uint32_t it = 0;
             for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
                 const int plane = tile / p.tiles_h, h0 = (tile % p.tiles_h) * p.TH;
@@ -88,14 +89,15 @@ conv3d_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                 const int s = it % STAGES;
                 mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
                 uint8_t* dst = smem + (size_t)s * stage_bytes;
-                mbar_arrive_expect_tx(&full_bar[s], 3 * p.x_tx + p.dy_tx);
+                if (leader) mbar_arrive_expect_tx(&full_bar[s], 3 * p.x_tx + p.dy_tx);
 #pragma unroll
-                for (int kd = 0; kd < 3; ++kd) tma5(dst + kd * p.x_region, &tmap_x, &full_bar[s], 0, -1, h0 - 1, d + kd - 1, n);
-                tma5(dst + 3 * p.x_region + 1024, &tmap_dy, &full_bar[s], 0, 0, h0, d, n);
+                for (int kd = 0; kd < 3; ++kd) if (leader) tma5(dst + kd * p.x_region, &tmap_x, &full_bar[s], 0, -1, h0 - 1, d + kd - 1, n);
+                if (leader) tma5(dst + 3 * p.x_region + 1024, &tmap_dy, &full_bar[s], 0, 0, h0, d, n);
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();   // whole warp runs the loop (uniform descriptors), one lane issues
             constexpr uint32_t idesc = make_idesc_f16(128, COUT, 1, 1, 1);          // both operands MN-major
             uint32_t it = 0;
             for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
@@ -115,13 +117,13 @@ conv3d_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                     const uint32_t a0 = xs16 + kd * region16 + kh * row16;
 #pragma unroll
                     for (int k = 0; k < 8; ++k)                                      // 16 pixels per MMA
-                        umma_f16(tmem_base + m * COUT, a_const | (a0 + k * PIXB), b_const | (dys16 + k * DYB), idesc,
+                        if (leader) umma_f16(tmem_base + m * COUT, a_const | (a0 + k * PIXB), b_const | (dys16 + k * DYB), idesc,
                                  (it > 0 || k > 0) ? 1u : 0u);
                     if (++kh == 3) { kh = 0; ++kd; }
                 }
-                umma_commit(&empty_bar[s]);
+                if (leader) umma_commit(&empty_bar[s]);
             }
-            umma_commit(done_bar);
+            if (leader) umma_commit(done_bar);
         }
     } else {
         const int q = warp & 3;

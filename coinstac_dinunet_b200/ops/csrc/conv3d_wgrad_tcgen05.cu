@@ -80,21 +80,23 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const WgradPara
 
     if (warp == 0) {
         // ============================ dy TMA producer ============================
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();   // whole warp runs the loop (uniform descriptors), one lane issues
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
-                mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES);
+                if (leader) mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES);
                 uint8_t* b_dst = smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES;
                 const int row0 = (int)(m_begin + (long long)kb * WG_BK);
 #pragma unroll
                 for (int j = 0; j < B_BLOCKS; ++j)
-                    tma_load_2d(b_dst + j * (WG_BK * 128), &tmap_dy, &full_bar[s], j * 64, row0);
+                    if (leader) tma_load_2d(b_dst + j * (WG_BK * 128), &tmap_dy, &full_bar[s], j * 64, row0);
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();   // whole warp runs the loop (uniform descriptors), one lane issues
             constexpr uint32_t idesc = make_idesc_f16(128, COUT, 1, 1, 1);      // A and B MN-major
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
@@ -110,12 +112,12 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const WgradPara
                         const uint64_t adesc = make_smem_desc(a_base + mt * Cfg::A_TILE + k * 2048, 8192, 1024, SMEM_LAYOUT_SW128);
                         const uint64_t bdesc = B_SW64 ? make_smem_desc(b_base + k * 1024, 4096, 512, SMEM_LAYOUT_SW64)
                                                       : make_smem_desc(b_base + k * 2048, 8192, 1024, SMEM_LAYOUT_SW128);
-                        umma_f16(tmem_base + mt * COUT, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        if (leader) umma_f16(tmem_base + mt * COUT, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                 }
-                umma_commit(&empty_bar[s]);
+                if (leader) umma_commit(&empty_bar[s]);
             }
-            umma_commit(done_bar);
+            if (leader) umma_commit(done_bar);
         }
     } else if (warp < 6) {
         // ================================= epilogue =================================

@@ -73,22 +73,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();   // whole warp runs the loop (uniform descriptors), one lane issues
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * S::STAGE_BYTES;
                 uint8_t* b_dst = a_dst + S::A_BYTES;
-                mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
+                if (leader) mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
                 const int k0 = (kb_begin + i) * GEMM_BK;
-                tma_load_2d(a_dst, &tmap_a, &full_bar[s], k0, m0);
-                tma_load_2d(b_dst, &tmap_b, &full_bar[s], k0, n0);
+                if (leader) tma_load_2d(a_dst, &tmap_a, &full_bar[s], k0, m0);
+                if (leader) tma_load_2d(b_dst, &tmap_b, &full_bar[s], k0, n0);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();   // whole warp runs the loop (uniform descriptors), one lane issues
             constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BLOCK_N, 1, 0, 0);
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
@@ -101,11 +103,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int k = 0; k < GEMM_BK / 16; ++k) {
                     const uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, 1024, SMEM_LAYOUT_SW128);
                     const uint64_t bdesc = make_smem_desc(b_addr + k * 32, 16, 1024, SMEM_LAYOUT_SW128);
-                    umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    if (leader) umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(&empty_bar[s]);          // smem slot reusable once these MMAs retire
+                if (leader) umma_commit(&empty_bar[s]);          // smem slot reusable once these MMAs retire
             }
-            umma_commit(tmem_full_bar);              // accumulator complete
+            if (leader) umma_commit(tmem_full_bar);              // accumulator complete
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
