@@ -35,14 +35,14 @@ class FSNet(_nn.Module):
     def forward(self, x):
         x = x.reshape(x.shape[0], -1)
         if self.native and x.is_cuda:
-            from ..ops.linear import LinearFn
+            from ..ops.linear import linear as _linear
             h = x
             for layer in self.features:
                 if isinstance(layer, _nn.Linear):
-                    h = LinearFn.apply(h, layer.weight, layer.bias, False).float()
+                    h = _linear(h, layer.weight, layer.bias, False).float()
                 else:
                     h = layer(h)
-            return LinearFn.apply(h, self.classifier.weight, self.classifier.bias, False).float()
+            return _linear(h, self.classifier.weight, self.classifier.bias, False).float()
         return self.classifier(self.features(x))
 
 

@@ -72,7 +72,7 @@ class VBMNet(_nn.Module):
         return self.classifier(self.head(z.flatten(1)))
 
     def _forward_native(self, x):
-        from ..ops.linear import LinearFn
+        from ..ops.linear import linear as _linear
         from ..ops.vbm import ConvBnReluPoolFn, conv1_fused_enabled
         h = x[:, 0] if x.dim() == 5 else x                     # [N, D, H, W]; C_in == 1
         if h.dtype != _torch.float32 and not (conv1_fused_enabled() and h.dtype == _torch.bfloat16):
@@ -88,8 +88,8 @@ class VBMNet(_nn.Module):
         z = h.permute(0, 4, 1, 2, 3).reshape(h.shape[0], -1)    # NCDHW flatten order == the torch path
         for layer in self.head:
             if isinstance(layer, _nn.Linear):
-                z = LinearFn.apply(z, layer.weight, layer.bias, True)
-        return LinearFn.apply(z, self.classifier.weight, self.classifier.bias, False).float()
+                z = _linear(z, layer.weight, layer.bias, True)
+        return _linear(z, self.classifier.weight, self.classifier.bias, False).float()
 
 
 class VBMDataset(ArrayFileDataset):

@@ -50,6 +50,7 @@ def conv_impl():
 
 
 #: which implementation served the last call (tests / profiling)
+stats_done = False
 last_impl = None
 
 
@@ -79,18 +80,23 @@ def pack_weights(weight):
     return bufs[0], kf, bufs[1], kd
 
 
-def _igemm(x, wk, kpad, cout, impl=None):
-    global last_impl
+def _igemm(x, wk, kpad, cout, impl=None, stats=None):
+    """``stats``: optional zeroed fp32 [2*cout]; filled with the BatchNorm sums of y by the halo kernel's epilogue
+    (returns False in ``stats_done`` when the kernel that ran cannot do it)."""
+    global last_impl, stats_done
     N, D, H, W, cin = x.shape
     y = _torch.empty((N, D, H, W, cout), dtype=BF16, device=x.device)
     impl = impl or conv_impl()
     lib = _nat.lib()
     args = (x.data_ptr(), wk.data_ptr(), y.data_ptr(), N, D, H, W, cin, cout, kpad, _nat.stream_ptr(x.device))
     code = -1
+    stats_done = False
     if impl in ('auto', 'halo', 'halo2'):
-        fullpix = 1 if impl == 'halo2' or (impl == 'auto' and _os.environ.get('COINN_HALO_FULLPIX', '0') == '1') else 0
-        code = lib.coinn_conv3d_halo(*args[:-1], fullpix, args[-1])
+        fullpix = 1 if impl == 'halo2' or (impl == 'auto' and _os.environ.get('COINN_HALO_FULLPIX', '1') == '1') else 0
+        want = stats is not None and cout <= 64
+        code = lib.coinn_conv3d_halo_stats(args[0], args[1], args[2], stats.data_ptr() if want else None, *args[3:-1], fullpix, args[-1])
         last_impl = 'halo2' if fullpix else 'halo'
+        stats_done = want and code == 0
     if code == -1 and impl != 'gather':
         code, last_impl = lib.coinn_conv3d_tma(*args), 'tma'
     if code == -1:
@@ -100,13 +106,17 @@ def _igemm(x, wk, kpad, cout, impl=None):
     return y
 
 
-def conv3d_igemm_fwd(x, weight):
+def conv3d_igemm_fwd(x, weight, want_stats=False):
     """x: [N,D,H,W,Cin] bf16 contiguous; weight: [Cout,Cin,3,3,3] -> [N,D,H,W,Cout] bf16."""
     cout, cin = weight.shape[:2]
     if not supported(cin, cout):
         raise ImportError(f'no tcgen05 conv instantiation for {cin}->{cout}')
     wk, kpad, _, _ = pack_weights(weight)
-    return _igemm(x.contiguous(), wk, kpad, cout)
+    if not want_stats:
+        return _igemm(x.contiguous(), wk, kpad, cout)
+    stats = _torch.zeros(2 * cout, dtype=_torch.float32, device=x.device)
+    y = _igemm(x.contiguous(), wk, kpad, cout, stats=stats)
+    return y, (stats if stats_done else None)
 
 
 def conv3d_igemm_bwd(dy, x, weight, need_dx=True):

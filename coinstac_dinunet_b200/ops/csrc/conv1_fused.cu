@@ -136,8 +136,8 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_xp);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 4; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&dy_ready[b], 4); mbar_init(&dy_free[b], 1); }
+        for (int b = 0; b < 4; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], MODE == C1F_BWD ? 8 : 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&dy_ready[b], 8); mbar_init(&dy_free[b], 1); }
         mbar_init(done_bar, 1);
         fence_mbar_init();
     }
@@ -390,81 +390,97 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams 
                 if (ew == 0 && lane == 0) cS[c] = S;
             }
             asm volatile("bar.sync 2, 256;" ::: "memory");               // the 8 epilogue warps
-            const uint32_t dy_addr = smem_u32(dy_smem) + (uint32_t)grp * C1F_DY_BYTES + (uint32_t)r * 128u;
+            const uint32_t dy_addr0 = smem_u32(dy_smem) + (uint32_t)r * 128u;
             const uint32_t sw = (uint32_t)(r & 7);
+            // Both epilogue groups work on EVERY half-block (group g owns voxel pairs 2g, 2g+1 = M block g of the dy tile):
+            // the latency of one half-block's epilogue - which the next wgrad MMAs wait for - is half of what it is when
+            // the groups alternate between half-blocks.
             uint32_t hb = 0;
             for (int u = first; u < p.num_units; u += step) {
                 int n, hp, t, g;
                 c1f_unit(p, u, n, hp, t, g);
                 const int nb = (p.nblk - g * p.bpg) < p.bpg ? (p.nblk - g * p.bpg) : p.bpg;
-                const int d = t * 128 + r, h = 2 * hp + grp;               // this group's line: A (grp 0) or B (grp 1)
-                const bool row_ok = d < p.D && h < p.H;
-                const bool cell_row_ok = row_ok && (d >> 1) < PD && (h >> 1) < PH;
-                const long long cell_row = (((long long)n * PD + (d >> 1)) * PH + (h >> 1)) * PW;
-                const uint32_t pos_dh = (uint32_t)(((d & 1) << 2) | ((h & 1) << 1)) | 8u;
-                for (int jj = 0; jj < nb; ++jj, hb += 2) {
-                    const uint32_t my = hb + (uint32_t)grp;                // half-block index handled by this group
-                    const uint32_t b = (uint32_t)grp;
+                const int d = t * 128 + r;
+                for (int jj = 0; jj < nb; ++jj) {
                     const int w0 = (g * p.bpg + jj) * 8;
-                    // all global loads of this half-block (arg-max codes + pooled gradients of its 4 pool cells) are issued
-                    // before the barrier waits: their latency hides behind the MMAs instead of stalling every iteration
-                    uint4 cdv[4], g0v[4], g1v[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int pw = (w0 >> 1) + i;
-                        cdv[i] = make_uint4(0u, 0u, 0u, 0u); g0v[i] = cdv[i]; g1v[i] = cdv[i];
-                        if (cell_row_ok && pw < PW) {
-                            const long long cell = cell_row + pw;
-                            cdv[i] = ld_global_nc_128(p.code + cell * 16);
-                            g0v[i] = ld_global_nc_128(p.dpool + cell * 16);
-                            g1v[i] = ld_global_nc_128(p.dpool + cell * 16 + 8);
-                        }
-                    }
-                    mbar_wait(&tmem_full[b], (my >> 1) & 1);
-                    mbar_wait(&dy_free[b], ((my >> 1) & 1) ^ 1);           // wgrad MMAs of the previous tile in this buffer are done
-                    tcgen05_after_sync();
+                    for (int ab = 0; ab < 2; ++ab, ++hb) {
+                        const int h = 2 * hp + ab;                         // line A / line B of the pair
+                        const bool row_ok = d < p.D && h < p.H;
+                        const bool cell_row_ok = row_ok && (d >> 1) < PD && (h >> 1) < PH;
+                        const long long cell_row = (((long long)n * PD + (d >> 1)) * PH + (h >> 1)) * PW;
+                        const uint32_t pos_dh = (uint32_t)(((d & 1) << 2) | ((h & 1) << 1)) | 8u;
+                        const uint32_t b = (uint32_t)ab;
+                        // the global loads of this half-block (arg-max codes + pooled gradients of this group's 2 pool cells)
+                        // are issued before the barrier waits: their latency hides behind the MMAs
+                        uint4 cdv[2], g0v[2], g1v[2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {                          // voxel pair (w0 + 2i, w0 + 2i + 1) shares one pool cell
-                        uint32_t v[2][16];
-                        tmem_ld_32x32b_x16(tmem_base + lane_off + b * 128 + (2 * i) * 16, v[0]);
-                        tmem_ld_32x32b_x16(tmem_base + lane_off + b * 128 + (2 * i + 1) * 16, v[1]);
-                        const uint4 cd = cdv[i], g0 = g0v[i], g1 = g1v[i];
-                        const uint32_t cdw[4] = {cd.x, cd.y, cd.z, cd.w};
-                        const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-                        float gsc[16];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float2 f = unpack_bf16x2(gw[c]);
-                            gsc[2 * c] = f.x * cS[2 * c]; gsc[2 * c + 1] = f.y * cS[2 * c + 1];
-                        }
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int w = w0 + 2 * i + e;
-                            const bool vox_ok = row_ok && w < p.W;
-                            const uint32_t match = pos_dh | (uint32_t)e;
-                            float o[16];
-#pragma unroll
-                            for (int c = 0; c < 16; ++c) {
-                                const bool hit = ((cdw[c >> 2] >> (8 * (c & 3))) & 0xFFu) == match;
-                                float t0 = fmaf(cB[c], __uint_as_float(v[e][c]), cA[c]);
-                                t0 += hit ? gsc[c] : 0.f;
-                                o[c] = vox_ok ? t0 : 0.f;
+                        for (int ii = 0; ii < 2; ++ii) {
+                            const int pw = (w0 >> 1) + 2 * grp + ii;
+                            cdv[ii] = make_uint4(0u, 0u, 0u, 0u); g0v[ii] = cdv[ii]; g1v[ii] = cdv[ii];
+                            if (cell_row_ok && pw < PW) {
+                                const long long cell = cell_row + pw;
+                                cdv[ii] = ld_global_nc_128(p.code + cell * 16);
+                                g0v[ii] = ld_global_nc_128(p.dpool + cell * 16);
+                                g1v[ii] = ld_global_nc_128(p.dpool + cell * 16 + 8);
                             }
-                            // voxel wl = 2i + e -> M block (wl >> 2), 16-byte chunks ((wl & 3) * 2, +1), 128B swizzle
-                            const uint32_t wl = (uint32_t)(2 * i + e);
-                            const uint32_t base = dy_addr + (wl >> 2) * 16384u;
-                            const uint32_t c0 = (wl & 3u) * 2u;
-                            st_shared_128(base + (((c0) ^ sw) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-                            st_shared_128(base + (((c0 + 1u) ^ sw) << 4), pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]),
-                                          pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
                         }
+                        if (ab == 0 && jj + 1 < nb && cell_row_ok) {        // next block's cells -> L1 (lines A and B share them)
+#pragma unroll
+                            for (int ii = 0; ii < 2; ++ii) {
+                                const int pw = (w0 >> 1) + 4 + 2 * grp + ii;
+                                if (pw < PW) {
+                                    asm volatile("prefetch.global.L1 [%0];" :: "l"(p.code + (cell_row + pw) * 16));
+                                    asm volatile("prefetch.global.L1 [%0];" :: "l"(p.dpool + (cell_row + pw) * 16));
+                                }
+                            }
+                        }
+                        mbar_wait(&tmem_full[b], (hb >> 1) & 1);
+                        mbar_wait(&dy_free[b], ((hb >> 1) & 1) ^ 1);       // wgrad MMAs of the previous tile in this buffer are done
+                        tcgen05_after_sync();
+                        const uint32_t dy_row = dy_addr0 + b * C1F_DY_BYTES + (uint32_t)grp * 16384u;
+#pragma unroll
+                        for (int ii = 0; ii < 2; ++ii) {                   // voxel pair (w0 + 2i, w0 + 2i + 1) shares one pool cell
+                            const int i = 2 * grp + ii;
+                            uint32_t v[2][16];
+                            tmem_ld_32x32b_x16(tmem_base + lane_off + b * 128 + (2 * i) * 16, v[0]);
+                            tmem_ld_32x32b_x16(tmem_base + lane_off + b * 128 + (2 * i + 1) * 16, v[1]);
+                            const uint4 cd = cdv[ii], g0 = g0v[ii], g1 = g1v[ii];
+                            const uint32_t cdw[4] = {cd.x, cd.y, cd.z, cd.w};
+                            const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                            float gsc[16];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float2 f = unpack_bf16x2(gw[c]);
+                                gsc[2 * c] = f.x * cS[2 * c]; gsc[2 * c + 1] = f.y * cS[2 * c + 1];
+                            }
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int w = w0 + 2 * i + e;
+                                const bool vox_ok = row_ok && w < p.W;
+                                const uint32_t match = pos_dh | (uint32_t)e;
+                                float o[16];
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) {
+                                    const bool hit = ((cdw[c >> 2] >> (8 * (c & 3))) & 0xFFu) == match;
+                                    float t0 = fmaf(cB[c], __uint_as_float(v[e][c]), cA[c]);
+                                    t0 += hit ? gsc[c] : 0.f;
+                                    o[c] = vox_ok ? t0 : 0.f;
+                                }
+                                // voxel wl = 2i + e -> M block (wl >> 2) == grp, 16-byte chunks ((wl & 3) * 2, +1), 128B swizzle
+                                const uint32_t c0 = (uint32_t)((2 * ii + e) * 2);
+                                st_shared_128(dy_row + (((c0) ^ sw) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                              pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                                st_shared_128(dy_row + (((c0 + 1u) ^ sw) << 4), pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]),
+                                              pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        tcgen05_before_sync();
+                        __syncwarp();
+                        if (lane == 0) { mbar_arrive(&tmem_empty[b]); mbar_arrive(&dy_ready[b]); }
                     }
-                    fence_proxy_async_smem();
-                    tcgen05_before_sync();
-                    __syncwarp();
-                    if (lane == 0) { mbar_arrive(&tmem_empty[b]); mbar_arrive(&dy_ready[b]); }
                 }
             }
             // ---- final: extract the 27 diagonals of the three accumulators and merge the CTAs

@@ -25,6 +25,7 @@ struct ConvHaloParams {
     uint32_t region_bytes;      // (TH+2) * Wp * 16, rounded up to 128
     uint32_t region_tx;         // exact bytes one halo box delivers
     int stages;
+    float* stats;               // optional [2*COUT]: per-channel sum / sum of squares of the stored (bf16) outputs, for BatchNorm
 };
 
 __device__ __forceinline__ void tma_load_5d_h(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
@@ -34,8 +35,8 @@ __device__ __forceinline__ void tma_load_5d_h(void* smem_dst, const CUtensorMap*
         :: "r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
-template <int CIN, int COUT, bool FULLPIX>
-__global__ void __launch_bounds__(CH_THREADS, 2)
+template <int CIN, int COUT, bool FULLPIX, bool STATS>
+__global__ void __launch_bounds__(CH_THREADS, STATS ? 1 : 2)
 conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const ConvHaloParams p) {
     // FULLPIX: one box per d-plane holding whole pixels (CIN*2 = 32/64 bytes, 32B/64B swizzle) - 2-4x fewer and
     // 2-4x larger TMA requests than the chunk-plane layout (8 channels = 16 B per request, no swizzle).
@@ -157,6 +158,12 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         const int q = warp & 3;
         const int pix = q * 32 + lane;
         const int hh = pix / p.Wp, ww = pix % p.Wp;
+        // BatchNorm batch statistics fused into the producer: the thread owns one pixel, i.e. all COUT channels
+        float s1[STATS ? COUT : 1], s2[STATS ? COUT : 1];
+        if (STATS) {
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+        }
         uint32_t it = 0;
         for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++it) {
             const uint32_t a = it & 1;
@@ -165,27 +172,37 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             __nv_bfloat16* out = p.y + (((long long)plane * p.H + h) * p.W + ww) * COUT;
             mbar_wait(&tmem_full[a], (it >> 1) & 1);
             tcgen05_after_sync();
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < COUT; c += 16) {
                 uint32_t r[16];
                 tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + a * COUT + c, r);
                 tmem_ld_wait();
                 if (ok) {
-                    uint4 lo = make_uint4(pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1])),
-                                          pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3])),
-                                          pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5])),
-                                          pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7])));
-                    uint4 hi = make_uint4(pack_bf16x2(__uint_as_float(r[8]), __uint_as_float(r[9])),
-                                          pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11])),
-                                          pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13])),
-                                          pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15])));
-                    *reinterpret_cast<uint4*>(out + c) = lo;
-                    *reinterpret_cast<uint4*>(out + c + 8) = hi;
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+                    *reinterpret_cast<uint4*>(out + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(out + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if (STATS) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float2 f = unpack_bf16x2(pk[e]);
+                            s1[c + 2 * e] += f.x; s2[c + 2 * e] = fmaf(f.x, f.x, s2[c + 2 * e]);
+                            s1[c + 2 * e + 1] += f.y; s2[c + 2 * e + 1] = fmaf(f.y, f.y, s2[c + 2 * e + 1]);
+                        }
+                    }
                 }
             }
             tcgen05_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[a]);
+        }
+        if (STATS) {
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) {
+                const float sa = warp_sum(s1[c]), sb = warp_sum(s2[c]);
+                if (lane == 0) { atomicAdd(&p.stats[c], sa); atomicAdd(&p.stats[COUT + c], sb); }
+            }
         }
     }
 
@@ -194,13 +211,14 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int CIN, int COUT, bool FULLPIX>
-static int launch_conv_halo(const void* x, const void* wk, void* y, int N, int D, int H, int W, int kpad, cudaStream_t st) {
+template <int CIN, int COUT, bool FULLPIX, bool STATS>
+static int launch_conv_halo(const void* x, const void* wk, void* y, float* stats, int N, int D, int H, int W, int kpad, cudaStream_t st) {
     constexpr int CHUNKS = CIN / 8, REGIONS = FULLPIX ? 3 : 3 * CHUNKS, KCH = 27 * CHUNKS;
     constexpr int PIXB = FULLPIX ? CIN * 2 : 16;
     constexpr uint32_t W_BYTES = (KCH * COUT * 16 + 1023) / 1024 * 1024;
     ConvHaloParams p;
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    p.stats = stats;
     p.N = N; p.D = D; p.H = H; p.W = W;
     p.Wp = W + 2;
     if (p.Wp > 128) return -1;
@@ -216,7 +234,7 @@ static int launch_conv_halo(const void* x, const void* wk, void* y, int N, int D
     // the weights + 3 halo stages fit twice: the per-tile latency chains of the two CTAs overlap
     static int ctas_env = -1;
     if (ctas_env < 0) { const char* e = getenv("COINN_HALO_CTAS"); ctas_env = e ? atoi(e) : 1; }   // measured: 2 CTAs/SM 161 us vs 1 CTA 154 us (layer-2 fprop): no gain
-    int ctas = (ctas_env >= 2 && p.num_tiles >= 4 * B200_SM_COUNT && 2 * COUT * 2 <= 256 &&
+    int ctas = (!STATS && ctas_env >= 2 && p.num_tiles >= 4 * B200_SM_COUNT && 2 * COUT * 2 <= 256 &&
                 (int)W_BYTES + 3 * (int)stage_bytes + 2048 <= 110 * 1024) ? 2 : 1;
     const int budget = (ctas == 2 ? 110 : 220) * 1024 - (int)W_BYTES - 1024 - 512;
     int stages = budget / (int)stage_bytes;
@@ -240,12 +258,12 @@ static int launch_conv_halo(const void* x, const void* wk, void* y, int N, int D
     if (make_tmap_2d_bf16(&tw, wk, (uint64_t)COUT, (uint64_t)kpad, (uint64_t)kpad * 2, COUT, 8, CU_TENSOR_MAP_SWIZZLE_NONE) != 0) return -4;
     static int configured = 0;
     if (configured < smem_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(conv3d_halo_kernel<CIN, COUT, FULLPIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(conv3d_halo_kernel<CIN, COUT, FULLPIX, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return (int)e;
         configured = smem_bytes;
     }
     const int grid = p.num_tiles < ctas * B200_SM_COUNT ? p.num_tiles : ctas * B200_SM_COUNT;
-    conv3d_halo_kernel<CIN, COUT, FULLPIX><<<grid, CH_THREADS, smem_bytes, st>>>(tx, tw, p);
+    conv3d_halo_kernel<CIN, COUT, FULLPIX, STATS><<<grid, CH_THREADS, smem_bytes, st>>>(tx, tw, p);
     COINN_CHECK_LAUNCH();
     return 0;
 }
@@ -254,15 +272,23 @@ static int launch_conv_halo(const void* x, const void* wk, void* y, int N, int D
 
 // same contract as coinn_conv3d_igemm; returns -1 when the shape is outside what the halo kernel covers
 // fullpix != 0 selects the whole-pixel (swizzled) halo layout, available for cin in {16, 32}
-COINN_API int coinn_conv3d_halo(const void* x, const void* wk, void* y, int N, int D, int H, int W, int cin, int cout,
-                                int kpad, int fullpix, void* stream) {
+// stats (optional, [2*cout] fp32, zeroed): per-channel sum / sum of squares of y for BatchNorm, cout <= 64 only (-1 otherwise)
+COINN_API int coinn_conv3d_halo_stats(const void* x, const void* wk, void* y, float* stats, int N, int D, int H, int W, int cin, int cout,
+                                      int kpad, int fullpix, void* stream) {
     using namespace coinn;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define CASE(CI, CO) if (cin == CI && cout == CO) return launch_conv_halo<CI, CO, false>(x, wk, y, N, D, H, W, kpad, st);
-#define CASEF(CI, CO) if (fullpix && cin == CI && cout == CO) return launch_conv_halo<CI, CO, true>(x, wk, y, N, D, H, W, kpad, st);
+#define CASE(CI, CO) if (cin == CI && cout == CO) return stats ? launch_conv_halo<CI, CO, false, true>(x, wk, y, stats, N, D, H, W, kpad, st) \
+                                                               : launch_conv_halo<CI, CO, false, false>(x, wk, y, nullptr, N, D, H, W, kpad, st);
+#define CASEF(CI, CO) if (fullpix && cin == CI && cout == CO) return stats ? launch_conv_halo<CI, CO, true, true>(x, wk, y, stats, N, D, H, W, kpad, st) \
+                                                                           : launch_conv_halo<CI, CO, true, false>(x, wk, y, nullptr, N, D, H, W, kpad, st);
     CASEF(16, 32) CASEF(32, 16) CASEF(32, 64) CASEF(16, 16) CASEF(32, 32)
     CASE(16, 32) CASE(32, 16) CASE(32, 64) CASE(64, 32) CASE(16, 16) CASE(32, 32)
 #undef CASE
 #undef CASEF
     return -1;
+}
+
+COINN_API int coinn_conv3d_halo(const void* x, const void* wk, void* y, int N, int D, int H, int W, int cin, int cout,
+                                int kpad, int fullpix, void* stream) {
+    return coinn_conv3d_halo_stats(x, wk, y, nullptr, N, D, H, W, cin, cout, kpad, fullpix, stream);
 }

@@ -454,15 +454,31 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_stats_pooled_kernel(const __n
         a0[j] = 0.f; a1[j] = 0.f;
     }
     if (my_row < rows_per_iter) {
-        for (long long m = (long long)blockIdx.x * rows_per_iter + my_row; m < cells; m += (long long)gridDim.x * rows_per_iter) {
-            float pv[8], gv[8];
-            unpack8(ld_stream_u4(reinterpret_cast<const uint4*>(p + m * C) + my_chunk), pv);
-            unpack8(ld_stream_u4(reinterpret_cast<const uint4*>(dp + m * C) + my_chunk), gv);
+        // 4 rows (8 independent 16-byte loads) in flight per thread: the single-row loop was bound by load latency
+        // (58 us for the 66 MB of layer 1, 10 us at the copy roofline)
+        const long long stride = (long long)gridDim.x * rows_per_iter;
+        for (long long m0 = (long long)blockIdx.x * rows_per_iter + my_row; m0 < cells; m0 += 4 * stride) {
+            uint4 pr[4], gr[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float g = pv[j] > 0.f ? gv[j] : 0.f;
-                a0[j] += g;
-                a1[j] = fmaf(g, (pv[j] - be[j]) * ig[j], a1[j]);
+            for (int u = 0; u < 4; ++u) {
+                const long long m = m0 + u * stride;
+                pr[u] = make_uint4(0u, 0u, 0u, 0u); gr[u] = pr[u];
+                if (m < cells) {
+                    pr[u] = ld_stream_u4(reinterpret_cast<const uint4*>(p + m * C) + my_chunk);
+                    gr[u] = ld_stream_u4(reinterpret_cast<const uint4*>(dp + m * C) + my_chunk);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float pv[8], gv[8];
+                unpack8(pr[u], pv);
+                unpack8(gr[u], gv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float g = pv[j] > 0.f ? gv[j] : 0.f;          // rows beyond the end were loaded as p = 0
+                    a0[j] += g;
+                    a1[j] = fmaf(g, (pv[j] - be[j]) * ig[j], a1[j]);
+                }
             }
         }
 #pragma unroll
@@ -664,7 +680,7 @@ COINN_API int coinn_bn_pool_bwd_stats_pooled(const void* p, const void* dp, cons
     if (cells == 0) return 0;
     const int rows_per_iter = 256 / (C / 8);
     long long want = (cells + (long long)rows_per_iter * 8 - 1) / ((long long)rows_per_iter * 8);
-    const int grid = (int)(want < 1 ? 1 : (want > 4LL * B200_SM_COUNT ? 4LL * B200_SM_COUNT : want));
+    const int grid = (int)(want < 1 ? 1 : (want > 8LL * B200_SM_COUNT ? 8LL * B200_SM_COUNT : want));
     bn_pool_bwd_stats_pooled_kernel<<<grid, 256, 2 * C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
         (const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, gamma, beta, acc, cells, C);
     COINN_CHECK_LAUNCH();

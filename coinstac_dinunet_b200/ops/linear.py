@@ -92,6 +92,77 @@ class LinearFn(_torch.autograd.Function):
         return dx, dw, db, None
 
 
+def direct_grad_ok(param):
+    """True when a backward kernel may accumulate straight into ``param.grad`` (fp32, contiguous, already allocated -
+    e.g. a view of the DistArena gradient arena) and return ``None`` to autograd: no temporary, no AccumulateGrad add.
+    COINN_DIRECT_GRAD=0 disables it (needed if post-accumulate-grad hooks must fire for every parameter)."""
+    import os
+    g = getattr(param, 'grad', None)
+    return (os.environ.get('COINN_DIRECT_GRAD', '1') != '0' and g is not None and param.dtype == _torch.float32
+            and g.dtype == _torch.float32 and g.is_contiguous() and param.is_contiguous())
+
+
+SMALL_M = 32
+
+
+class SmallLinearFn(_torch.autograd.Function):
+    """y = relu?(x @ W^T + b) for M <= 32 rows on the CUDA-core kernels of ``csrc/linear_small.cu`` (two launches per
+    layer and step instead of ~15; fp32 weights are streamed once, dW/db accumulate in place into ``.grad``)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        if x.dtype not in (_torch.float32, _torch.bfloat16):
+            x = x.float()
+        x = x.contiguous()
+        w = weight.detach()
+        w = w if (w.dtype == _torch.float32 and w.is_contiguous()) else w.float().contiguous()
+        b = None if bias is None else bias.detach().float().contiguous()
+        M, K = x.shape
+        N = w.shape[0]
+        y = _torch.empty((M, N), dtype=_torch.float32, device=x.device)
+        _nat.check(_nat.lib().coinn_linear_small_fwd(x.data_ptr(), 1 if x.dtype == _torch.bfloat16 else 0, w.data_ptr(),
+                                                     b.data_ptr() if b is not None else None, y.data_ptr(), M, N, K, int(relu),
+                                                     _nat.stream_ptr(x.device)), 'coinn_linear_small_fwd')
+        _bump()
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.params = (weight, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        weight, bias = ctx.params
+        M, K = x.shape
+        N = w.shape[0]
+        dy = dy.float().contiguous()
+        need_w, need_b = ctx.needs_input_grad[1], bias is not None and ctx.needs_input_grad[2]
+        direct = need_w and direct_grad_ok(weight) and w.data_ptr() == weight.data_ptr() and (not need_b or direct_grad_ok(bias))
+        if direct:
+            dw, db = weight.grad, (bias.grad if need_b else None)
+        else:
+            dw = _torch.zeros((N, K), dtype=_torch.float32, device=x.device)
+            db = _torch.zeros(N, dtype=_torch.float32, device=x.device) if need_b else None
+        dx = _torch.zeros((M, K), dtype=_torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
+        _nat.check(_nat.lib().coinn_linear_small_bwd(dy.data_ptr(), y.data_ptr() if y is not None else None, x.data_ptr(),
+                                                     1 if x.dtype == _torch.bfloat16 else 0, w.data_ptr(), dw.data_ptr(),
+                                                     db.data_ptr() if db is not None else None,
+                                                     dx.data_ptr() if dx is not None else None, M, N, K,
+                                                     _nat.stream_ptr(x.device)), 'coinn_linear_small_bwd')
+        _bump()
+        if dx is not None and x.dtype != _torch.float32:
+            dx = dx.to(x.dtype)
+        if direct:
+            return dx, None, None, None
+        return dx, dw.to(weight.dtype), (db.to(bias.dtype) if db is not None else None), None
+
+
+def linear(x, weight, bias, relu):
+    """Dispatch: small-batch CUDA-core kernels (M <= 32) or the tcgen05 GEMM path."""
+    if x.shape[0] <= SMALL_M:
+        return SmallLinearFn.apply(x, weight, bias, relu)
+    return LinearFn.apply(x, weight, bias, relu)
+
+
 class B200Linear(_torch.nn.Linear):
     """Drop-in ``nn.Linear`` whose forward/backward run on the tcgen05 GEMM (optionally with the
     following ReLU fused into the epilogue)."""
@@ -115,5 +186,5 @@ class B200Linear(_torch.nn.Linear):
             y = _torch.nn.functional.linear(x, self.weight, self.bias)
             return y.relu() if self.fuse_relu else y
         lead = x.shape[:-1]
-        y = LinearFn.apply(x.reshape(-1, x.shape[-1]), self.weight, self.bias, self.fuse_relu)
+        y = linear(x.reshape(-1, x.shape[-1]), self.weight, self.bias, self.fuse_relu)
         return y.reshape(*lead, self.out_features)

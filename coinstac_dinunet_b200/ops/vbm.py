@@ -222,8 +222,18 @@ def _as_ncdhw(x_ndhwc):
     return x_ndhwc.permute(0, 4, 1, 2, 3)          # logical NCDHW, channels_last_3d strides (no copy)
 
 
-def conv3d_fwd(x, weight, backend='auto'):
-    """x: [N,D,H,W,Cin] bf16, weight: [Cout,Cin,3,3,3] (any float dtype) -> y [N,D,H,W,Cout] bf16."""
+def conv3d_fwd(x, weight, backend='auto', want_stats=False):
+    """x: [N,D,H,W,Cin] bf16, weight: [Cout,Cin,3,3,3] (any float dtype) -> y [N,D,H,W,Cout] bf16.
+    ``want_stats``: -> (y, stats or None); stats = BatchNorm sums produced by the conv epilogue when the kernel can."""
+    if want_stats:
+        if backend in ('auto', 'tcgen05'):
+            try:
+                from .conv3d import conv3d_igemm_fwd
+                return conv3d_igemm_fwd(x, weight, want_stats=True)
+            except ImportError:
+                if backend == 'tcgen05':
+                    raise
+        return conv3d_fwd(x, weight, backend), None
     if backend in ('auto', 'tcgen05'):
         try:
             from .conv3d import conv3d_igemm_fwd
@@ -278,8 +288,7 @@ class ConvBnReluPoolFn(_torch.autograd.Function):
         if first:
             y, stats = conv1_fwd(x, conv_w)
         else:
-            y = conv3d_fwd(x, conv_w, backend)
-            stats = None
+            y, stats = conv3d_fwd(x, conv_w, backend, want_stats=bool(training))
         N, D, H, W, C = y.shape
         if training:
             if stats is None:

@@ -507,3 +507,51 @@ def test_conv1_fused_block_backward(dev, shape):
     assert float(cos) > 0.999 and _rel(wq.grad, ref['dw']) < 3e-2, (float(cos), _rel(wq.grad, ref['dw']))
     assert _rel(gq.grad, ref['dgamma']) < 3e-2 and _rel(bq.grad, ref['dbeta']) < 3e-2
     assert torch.allclose(rm, 0.1 * ref['mean'], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize('cin,cout,shape', [(16, 32, (2, 6, 9, 20)), (32, 64, (1, 5, 7, 30)), (32, 16, (2, 4, 6, 11))])
+def test_conv3d_halo_fused_bn_stats(dev, cin, cout, shape):
+    """the halo conv epilogue also produces the BatchNorm sums of the stored output (no separate pass over y)."""
+    from coinstac_dinunet_b200.ops import conv3d as c3
+    torch.manual_seed(8)
+    N, D, H, W = shape
+    x = torch.randn(N, D, H, W, cin, device=dev).bfloat16()
+    w = torch.randn(cout, cin, 3, 3, 3, device=dev) * 0.05
+    y0 = c3.conv3d_igemm_fwd(x, w)
+    y, stats = c3.conv3d_igemm_fwd(x, w, want_stats=True)
+    assert stats is not None and torch.equal(y, y0)
+    yf = y.float().reshape(-1, cout)
+    assert torch.allclose(stats[:cout], yf.sum(0), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(stats[cout:], (yf * yf).sum(0), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize('M,K,N,relu,xdt', [(8, 9216, 256, True, torch.bfloat16), (16, 66, 256, False, torch.float32),
+                                             (3, 64, 2, False, torch.float32), (32, 130, 33, True, torch.float32)])
+def test_small_linear_matches_torch_and_accumulates_in_place(dev, M, K, N, relu, xdt):
+    """linear_small.cu: forward/backward vs fp32 torch; dW/db accumulate directly into pre-existing .grad buffers."""
+    from coinstac_dinunet_b200.ops.linear import SmallLinearFn
+    torch.manual_seed(12)
+    lin = torch.nn.Linear(K, N).to(dev)
+    x0 = torch.randn(M, K, device=dev).to(xdt)
+    xr = x0.float().clone().requires_grad_(True)
+    yr = torch.nn.functional.linear(xr, lin.weight, lin.bias)
+    yr = yr.relu() if relu else yr
+    g = torch.randn_like(yr)
+    gw, gb, gx = torch.autograd.grad(yr, [lin.weight, lin.bias, xr], g)
+    # direct accumulation: .grad exists and already holds something
+    lin.weight.grad = torch.full_like(lin.weight, 0.5)
+    lin.bias.grad = torch.full_like(lin.bias, -0.25)
+    wp, bp = lin.weight.grad.data_ptr(), lin.bias.grad.data_ptr()
+    x1 = x0.clone().requires_grad_(True)
+    y = SmallLinearFn.apply(x1, lin.weight, lin.bias, relu)
+    assert torch.allclose(y, yr, rtol=2e-4, atol=2e-4)
+    y.backward(g)
+    assert lin.weight.grad.data_ptr() == wp and lin.bias.grad.data_ptr() == bp
+    assert torch.allclose(lin.weight.grad - 0.5, gw, rtol=2e-3, atol=2e-4)
+    assert torch.allclose(lin.bias.grad + 0.25, gb, rtol=2e-3, atol=2e-4)
+    assert _rel(x1.grad, gx) < (1e-2 if xdt == torch.bfloat16 else 1e-4)
+    # fallback: no .grad yet -> ordinary autograd accumulation
+    lin.weight.grad = None; lin.bias.grad = None
+    x2 = x0.clone().requires_grad_(True)
+    SmallLinearFn.apply(x2, lin.weight, lin.bias, relu).backward(g)
+    assert torch.allclose(lin.weight.grad, gw, rtol=2e-3, atol=2e-4) and torch.allclose(lin.bias.grad, gb, rtol=2e-3, atol=2e-4)
