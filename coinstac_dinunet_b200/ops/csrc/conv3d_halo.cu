@@ -65,6 +65,8 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int STAGES = p.stages;
+    __shared__ float stat_red[STATS ? 2 * COUT : 1];
+    if (STATS && threadIdx.x < 2 * COUT) stat_red[threadIdx.x] = 0.f;
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_x);
         tma_prefetch_desc(&tmap_w);
@@ -201,13 +203,16 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 #pragma unroll
             for (int c = 0; c < COUT; ++c) {
                 const float sa = warp_sum(s1[c]), sb = warp_sum(s2[c]);
-                if (lane == 0) { atomicAdd(&p.stats[c], sa); atomicAdd(&p.stats[COUT + c], sb); }
+                if (lane == 0) { atomicAdd(&stat_red[c], sa); atomicAdd(&stat_red[COUT + c], sb); }
             }
         }
     }
 
     tcgen05_before_sync();
     __syncthreads();
+    // one global atomic per channel and CTA (same-address atomics serialise in L2: 4 warps x 148 CTAs x 2*COUT of them
+    // cost as much as the separate statistics pass they replace)
+    if (STATS && threadIdx.x < 2 * COUT) atomicAdd(&p.stats[threadIdx.x], stat_red[threadIdx.x]);
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 

@@ -12,6 +12,7 @@
 // once instead of 27 times (the gather kernel conv3d_wgrad_tcgen05.cu is bound by exactly that traffic).
 // Accumulators stay in TMEM across all tiles of the persistent CTA; fp32 atomics merge the CTAs at the end.
 #include "umma.cuh"
+#include <cstdlib>
 
 namespace coinn {
 
@@ -25,6 +26,7 @@ struct WgradHaloParams {
     uint32_t x_tx, dy_tx;       // exact bytes delivered by one x plane box / the dy box
     int stages;
     int mt_begin, mt_count;     // unused (grid.x selects the M-tile group)
+    int m64;                    // CIN == 16 only: 64-row MMAs (4 shift blocks instead of 8: half the A-operand smem traffic)
 };
 
 __device__ __forceinline__ void tma5(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
@@ -98,7 +100,9 @@ conv3d_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     } else if (warp == 1) {
         {
             const bool leader = elect_one();   // whole warp runs the loop (uniform descriptors), one lane issues
-            constexpr uint32_t idesc = make_idesc_f16(128, COUT, 1, 1, 1);          // both operands MN-major
+            // both operands MN-major.  With CIN = 16 an M = 128 MMA carries 8 pixel-shift blocks of which only 3 (kw) are
+            // used; M = 64 carries 4.  The kernel is bound by the shared-memory reads of the A operand, so M = 64 wins.
+            const uint32_t idesc = make_idesc_f16(p.m64 ? 64 : 128, COUT, 1, 1, 1);
             uint32_t it = 0;
             for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
                 const int s = it % STAGES;
@@ -127,7 +131,9 @@ conv3d_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         }
     } else {
         const int q = warp & 3;
-        const int l = q * 32 + lane;                                  // accumulator row = (shift j, channel ci)
+        // accumulator row = (shift j, channel ci).  M = 128: row r sits in TMEM lane r.  M = 64 (cta_group::1): rows
+        // 16q .. 16q+15 sit in lanes 32q .. 32q+15, i.e. warp q holds shift j = q in its first 16 lanes.
+        const int l = p.m64 ? (lane < 16 ? q * 16 + lane : 3 * CIN) : q * 32 + lane;
         const int j = l / CIN, ci = l % CIN;
         if (my_tiles > 0) {
             mbar_wait(done_bar, 0);
@@ -158,6 +164,9 @@ conv3d_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 template <int CIN, int COUT, int MT_MAX>
 static int launch_wgrad_halo(const void* x, const void* dy, float* dwt, int N, int D, int H, int W, cudaStream_t st) {
     WgradHaloParams p;
+    static int m64_env = -1;
+    if (m64_env < 0) { const char* e = getenv("COINN_WGRAD_M64"); m64_env = e ? atoi(e) : 1; }
+    p.m64 = (CIN == 16 && m64_env) ? 1 : 0;
     p.dwt = dwt; p.N = N; p.D = D; p.H = H; p.W = W;
     p.Wp = W + 2;
     if (p.Wp > 128) return -1;

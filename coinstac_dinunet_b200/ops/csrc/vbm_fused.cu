@@ -481,6 +481,20 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_stats_pooled_kernel(const __n
                 }
             }
         }
+    }
+    // lanes l, l + chunks, l + 2*chunks, ... of a warp hold the same channel chunk: butterfly over those first, so only
+    // `chunks` lanes per warp touch shared memory (128 threads hammering 16 addresses serialised the old epilogue), and
+    // a small grid keeps the same-address global atomics short (1184 CTAs x 32 atomics cost more than the 66 MB read)
+    if (chunks <= 32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            for (int off = 16; off >= chunks; off >>= 1) {
+                a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], off);
+                a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], off);
+            }
+        }
+    }
+    if (my_row < rows_per_iter && (chunks > 32 || (threadIdx.x & 31) < chunks)) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             atomicAdd(&sm[my_chunk * 8 + j], a0[j]);
@@ -680,7 +694,7 @@ COINN_API int coinn_bn_pool_bwd_stats_pooled(const void* p, const void* dp, cons
     if (cells == 0) return 0;
     const int rows_per_iter = 256 / (C / 8);
     long long want = (cells + (long long)rows_per_iter * 8 - 1) / ((long long)rows_per_iter * 8);
-    const int grid = (int)(want < 1 ? 1 : (want > 8LL * B200_SM_COUNT ? 8LL * B200_SM_COUNT : want));
+    const int grid = (int)(want < 1 ? 1 : (want > 2LL * B200_SM_COUNT ? 2LL * B200_SM_COUNT : want));
     bn_pool_bwd_stats_pooled_kernel<<<grid, 256, 2 * C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
         (const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, gamma, beta, acc, cells, C);
     COINN_CHECK_LAUNCH();
