@@ -82,9 +82,7 @@ class VBMNet(_nn.Module):
             bn = blk.bn
             h = ConvBnReluPoolFn.apply(h, blk.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                        bn.eps, bn.momentum if bn.momentum is not None else 0.1, self.training,
-                                       self.conv_backend)
-            if self.training and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
+                                       self.conv_backend, bn.num_batches_tracked if self.training else None)
         z = h.permute(0, 4, 1, 2, 3).reshape(h.shape[0], -1)    # NCDHW flatten order == the torch path
         for layer in self.head:
             if isinstance(layer, _nn.Linear):

@@ -106,7 +106,7 @@ def _igemm(x, wk, kpad, cout, impl=None, stats=None):
     return y
 
 
-def conv3d_igemm_fwd(x, weight, want_stats=False):
+def conv3d_igemm_fwd(x, weight, want_stats=False, stats_out=None):
     """x: [N,D,H,W,Cin] bf16 contiguous; weight: [Cout,Cin,3,3,3] -> [N,D,H,W,Cout] bf16."""
     cout, cin = weight.shape[:2]
     if not supported(cin, cout):
@@ -114,12 +114,12 @@ def conv3d_igemm_fwd(x, weight, want_stats=False):
     wk, kpad, _, _ = pack_weights(weight)
     if not want_stats:
         return _igemm(x.contiguous(), wk, kpad, cout)
-    stats = _torch.zeros(2 * cout, dtype=_torch.float32, device=x.device)
+    stats = stats_out if stats_out is not None else _torch.zeros(2 * cout, dtype=_torch.float32, device=x.device)
     y = _igemm(x.contiguous(), wk, kpad, cout, stats=stats)
     return y, (stats if stats_done else None)
 
 
-def conv3d_igemm_bwd(dy, x, weight, need_dx=True):
+def conv3d_igemm_bwd(dy, x, weight, need_dx=True, raw_dw=None):
     cout, cin = weight.shape[:2]
     if not supported(cout, cin):
         raise ImportError(f'no tcgen05 conv instantiation for dgrad {cout}->{cin}')
@@ -133,7 +133,7 @@ def conv3d_igemm_bwd(dy, x, weight, need_dx=True):
         dx = _igemm(dy.contiguous(), wd, kpad, cin)
     try:
         from .conv3d_wgrad import conv3d_wgrad
-        dw = conv3d_wgrad(dy, x)
+        dw = conv3d_wgrad(dy, x, raw_out=raw_dw)
     except ImportError:
         # interim: cuDNN weight gradient (library) until the tcgen05 wgrad kernel lands
         w = weight.detach().to(BF16).contiguous(memory_format=_torch.channels_last_3d)

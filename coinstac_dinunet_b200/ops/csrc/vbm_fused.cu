@@ -171,13 +171,16 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
 }
 
 // mean / invstd from sums; optionally update running stats (PyTorch semantics: unbiased running var)
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __restrict__ mean, float* __restrict__ invstd,
+__global__ void bn_finalize_kernel(float* __restrict__ stats, float* __restrict__ mean, float* __restrict__ invstd,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float count, float eps, float momentum, int C) {
+                                   float count, float eps, float momentum, int C, long long* __restrict__ num_batches_tracked,
+                                   int zero_stats) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
     if (c >= C) return;
     const float mu = stats[c] / count;
     const float var = fmaxf(stats[C + c] / count - mu * mu, 0.f);
+    if (zero_stats) { stats[c] = 0.f; stats[C + c] = 0.f; }   // persistent accumulator: ready for the next step, no memset launch
     mean[c] = mu;
     invstd[c] = rsqrtf(var + eps);
     if (running_mean) {
@@ -637,7 +640,57 @@ COINN_API int coinn_bn_stats(const void* y, float* stats, long long M, int C, vo
 COINN_API int coinn_bn_finalize(const float* stats, float* mean, float* invstd, float* running_mean, float* running_var,
                                 float count, float eps, float momentum, int C, void* stream) {
     coinn::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        stats, mean, invstd, running_mean, running_var, count, eps, momentum, C);
+        const_cast<float*>(stats), mean, invstd, running_mean, running_var, count, eps, momentum, C, nullptr, 0);
+    COINN_CHECK_LAUNCH();
+    return 0;
+}
+
+// + num_batches_tracked += 1 (optional) and re-zeroing of the (persistent) stats accumulator in the same launch
+COINN_API int coinn_bn_finalize2(float* stats, float* mean, float* invstd, float* running_mean, float* running_var,
+                                 float count, float eps, float momentum, int C, long long* num_batches_tracked, int zero_stats,
+                                 void* stream) {
+    coinn::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        stats, mean, invstd, running_mean, running_var, count, eps, momentum, C, num_batches_tracked, zero_stats);
+    COINN_CHECK_LAUNCH();
+    return 0;
+}
+
+// End of a conv block's backward, ONE launch instead of a permute copy, three AccumulateGrad adds and two memsets:
+//   w_grad[co][ci][tap] += dwt[(tap*cin + ci)*cout + co]   (transposed != 0; the tcgen05 wgrad kernels' layout)
+//   w_grad[i]           += dwt[i]                          (transposed == 0; conv1: already [co][tap])
+//   gamma_grad += acc[C:2C], beta_grad += acc[0:C]; dwt and acc are zeroed for the next step (persistent accumulators)
+namespace coinn {
+__global__ void conv_block_grad_finalize_kernel(float* __restrict__ dwt, float* __restrict__ acc, float* __restrict__ w_grad,
+                                                float* __restrict__ gamma_grad, float* __restrict__ beta_grad, int cin, int cout,
+                                                int transposed) {
+    const int total = 27 * cin * cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const float v = dwt[i];                              // coalesced read of the accumulator
+        dwt[i] = 0.f;
+        int dst = i;
+        if (transposed) {
+            const int co = i % cout, r = i / cout, ci = r % cin, tap = r / cin;
+            dst = (co * cin + ci) * 27 + tap;
+        }
+        w_grad[dst] += v;
+    }
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < cout; c += blockDim.x) {
+            beta_grad[c] += acc[c];
+            gamma_grad[c] += acc[cout + c];
+            acc[c] = 0.f; acc[cout + c] = 0.f;
+        }
+    }
+}
+}  // namespace coinn
+
+COINN_API int coinn_conv_block_grad_finalize(float* dwt, float* acc, float* w_grad, float* gamma_grad, float* beta_grad, int cin, int cout,
+                                             int transposed, void* stream) {
+    const int total = 27 * cin * cout;
+    int grid = (total + 255) / 256;
+    if (grid > 2 * B200_SM_COUNT) grid = 2 * B200_SM_COUNT;
+    coinn::conv_block_grad_finalize_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dwt, acc, w_grad, gamma_grad, beta_grad,
+                                                                                                     cin, cout, transposed);
     COINN_CHECK_LAUNCH();
     return 0;
 }

@@ -43,6 +43,8 @@ class _Lib:
         d.coinn_conv1_fwd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_bn_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
         d.coinn_bn_finalize.argtypes = [C.c_void_p] * 5 + [C.c_float] * 3 + [C.c_int, C.c_void_p]
+        d.coinn_bn_finalize2.argtypes = [C.c_void_p] * 5 + [C.c_float] * 3 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        d.coinn_conv_block_grad_finalize.argtypes = [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p]
         d.coinn_bn_relu_pool_fwd.argtypes = [C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p]
         d.coinn_bn_relu_pool_bwd.argtypes = [C.c_void_p] * 8 + [C.c_int] * 6 + [C.c_void_p]
         d.coinn_conv3d_igemm.argtypes = [C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p]

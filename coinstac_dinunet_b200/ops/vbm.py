@@ -63,6 +63,46 @@ def conv1_pad_input(x):
     return xp
 
 
+_SCRATCH = {}
+
+
+def _scratch(param, name, numel):
+    """Persistent zero-initialised fp32 accumulator tied to a parameter.  Its consumer kernel re-zeroes it in the launch
+    that reads it (bn_finalize2 / conv_block_grad_finalize), so a training step issues no memset for it."""
+    key = (param.data_ptr(), name, numel, param.device)
+    buf = _SCRATCH.get(key)
+    if buf is None:
+        buf = _torch.zeros(numel, dtype=_torch.float32, device=param.device)
+        _SCRATCH[key] = buf
+    return buf
+
+
+def _direct_ok(*params):
+    from .linear import direct_grad_ok
+    return all(direct_grad_ok(q) for q in params)
+
+
+def bn_finalize2(stats, count, eps, momentum, running_mean, running_var, nbt=None):
+    """bn_finalize + ``num_batches_tracked += 1`` + re-zeroing of the persistent ``stats`` accumulator, one launch."""
+    C = stats.numel() // 2
+    mean = _torch.empty(C, dtype=_torch.float32, device=stats.device)
+    invstd = _torch.empty_like(mean)
+    _chk(_nat.lib().coinn_bn_finalize2(stats.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                       running_mean.data_ptr() if running_mean is not None else None,
+                                       running_var.data_ptr() if running_var is not None else None,
+                                       float(count), float(eps), float(momentum), C,
+                                       nbt.data_ptr() if nbt is not None else None, 1, _sp(stats)), 'coinn_bn_finalize2')
+    _bump()
+    return mean, invstd
+
+
+def conv_block_grad_finalize(dwt, acc, conv_w, gamma, beta, cin, cout, transposed):
+    _chk(_nat.lib().coinn_conv_block_grad_finalize(dwt.data_ptr(), acc.data_ptr(), conv_w.grad.data_ptr(), gamma.grad.data_ptr(),
+                                                   beta.grad.data_ptr(), cin, cout, int(transposed), _sp(dwt)),
+         'coinn_conv_block_grad_finalize')
+    _bump()
+
+
 def conv1_fused_enabled():
     """First block without its full-resolution tensors (conv1_fused.cu): conv recomputed in the pool and backward
     kernels instead of stored.  COINN_CONV1_FUSED=0 falls back to conv1_fwd / bn_relu_pool_* / conv1_wgrad."""
@@ -86,10 +126,10 @@ def _w27(weight):
     return weight.detach().float().reshape(16, 27).contiguous()
 
 
-def conv1_fused_stats(xp, weight, shape):
+def conv1_fused_stats(xp, weight, shape, out=None):
     """-> stats[32]: per-channel sum and sum of squares of conv1(x) over the whole batch (nothing else is written)."""
     N, D, H, W = shape
-    stats = _torch.zeros(32, dtype=_torch.float32, device=xp.device)
+    stats = out if out is not None else _torch.zeros(32, dtype=_torch.float32, device=xp.device)
     _chk(_nat.lib().coinn_conv1_fused_stats(xp.data_ptr(), _w27(weight).data_ptr(), stats.data_ptr(), N, D, H, W, _sp(xp)),
          'coinn_conv1_fused_stats')
     _bump()
@@ -108,15 +148,15 @@ def conv1_fused_pool(xp, weight, mean, invstd, gamma, beta, shape):
     return p, code
 
 
-def conv1_fused_bwd(xp, weight, mean, invstd, gamma, beta, p, code, dp, shape):
+def conv1_fused_bwd(xp, weight, mean, invstd, gamma, beta, p, code, dp, shape, acc=None, dw=None):
     """-> (dW1 [16,1,3,3,3] fp32, dgamma, dbeta): BN/ReLU/pool backward + weight gradient with the conv output
     recomputed on the tensor cores and its gradient kept in shared memory (never in HBM)."""
     N, D, H, W = shape
     dp = dp.contiguous()
-    acc = _torch.zeros(32, dtype=_torch.float32, device=xp.device)
+    acc = acc if acc is not None else _torch.zeros(32, dtype=_torch.float32, device=xp.device)
     _chk(_nat.lib().coinn_bn_pool_bwd_stats_pooled(p.data_ptr(), dp.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                                    acc.data_ptr(), p.numel() // 16, 16, _sp(xp)), 'bn_pool_bwd_stats_pooled')
-    dw = _torch.zeros(16 * 27, dtype=_torch.float32, device=xp.device)
+    dw = dw if dw is not None else _torch.zeros(16 * 27, dtype=_torch.float32, device=xp.device)
     _chk(_nat.lib().coinn_conv1_fused_bwd(xp.data_ptr(), _w27(weight).data_ptr(), mean.data_ptr(), invstd.data_ptr(),
                                           gamma.data_ptr(), acc.data_ptr(), dp.data_ptr(), code.data_ptr(), dw.data_ptr(),
                                           N, D, H, W, _sp(xp)), 'coinn_conv1_fused_bwd')
@@ -167,10 +207,10 @@ def conv1_wgrad(dy, x, impl=None):
     return dw.view(16, 1, 3, 3, 3)
 
 
-def bn_stats(y):
+def bn_stats(y, out=None):
     """[..., C] bf16 -> stats[2C] = (sum, sumsq) over all leading dims."""
     C = y.shape[-1]
-    stats = _torch.zeros(2 * C, dtype=_torch.float32, device=y.device)
+    stats = out if out is not None else _torch.zeros(2 * C, dtype=_torch.float32, device=y.device)
     _chk(_nat.lib().coinn_bn_stats(y.data_ptr(), stats.data_ptr(), y.numel() // C, C, _sp(y)), 'coinn_bn_stats')
     _bump()
     return stats
@@ -197,13 +237,13 @@ def bn_relu_pool_fwd(y, mean, invstd, gamma, beta):
     return p
 
 
-def bn_relu_pool_bwd(y, dp, mean, invstd, gamma, beta, p=None):
+def bn_relu_pool_bwd(y, dp, mean, invstd, gamma, beta, p=None, acc=None):
     """-> (dy [N,D,H,W,C] bf16, dgamma [C], dbeta [C]).
 
     With the pooled forward output ``p`` given, pass A (dgamma / dbeta) runs on the pooled tensors only
     (xhat at the arg-max is recovered as (p - beta) / gamma): 1/8 of the bytes of the y-based pass."""
     N, D, H, W, C = y.shape
-    acc = _torch.zeros(2 * C, dtype=_torch.float32, device=y.device)
+    acc = acc if acc is not None else _torch.zeros(2 * C, dtype=_torch.float32, device=y.device)
     dy = _torch.empty_like(y)
     args = (y.data_ptr(), dp.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
             acc.data_ptr())
@@ -222,14 +262,14 @@ def _as_ncdhw(x_ndhwc):
     return x_ndhwc.permute(0, 4, 1, 2, 3)          # logical NCDHW, channels_last_3d strides (no copy)
 
 
-def conv3d_fwd(x, weight, backend='auto', want_stats=False):
+def conv3d_fwd(x, weight, backend='auto', want_stats=False, stats_out=None):
     """x: [N,D,H,W,Cin] bf16, weight: [Cout,Cin,3,3,3] (any float dtype) -> y [N,D,H,W,Cout] bf16.
     ``want_stats``: -> (y, stats or None); stats = BatchNorm sums produced by the conv epilogue when the kernel can."""
     if want_stats:
         if backend in ('auto', 'tcgen05'):
             try:
                 from .conv3d import conv3d_igemm_fwd
-                return conv3d_igemm_fwd(x, weight, want_stats=True)
+                return conv3d_igemm_fwd(x, weight, want_stats=True, stats_out=stats_out)
             except ImportError:
                 if backend == 'tcgen05':
                     raise
@@ -266,18 +306,36 @@ def conv3d_bwd(dy, x, weight, need_dx=True, backend='auto'):
 
 # --------------------------------------------------------------------------------- autograd
 class ConvBnReluPoolFn(_torch.autograd.Function):
-    """One fused VBM block.  ``x``: [N,D,H,W,Cin] bf16 (or [N,D,H,W] fp32/bf16 for the first block)."""
+    """One fused VBM block.  ``x``: [N,D,H,W,Cin] bf16 (or [N,D,H,W] fp32/bf16 for the first block).
+
+    When the three parameters already own fp32 ``.grad`` buffers (the DistArena gradient arena) the block runs in
+    "direct" mode: BatchNorm sums, BN-backward sums and the raw weight gradient live in persistent accumulators that their
+    consumer kernels re-zero, ``num_batches_tracked`` is bumped by ``bn_finalize2`` and one ``conv_block_grad_finalize``
+    launch folds everything into the ``.grad`` buffers - the block returns ``None`` for its parameter gradients and a
+    training step issues no memset / permute / AccumulateGrad launches for it."""
 
     @staticmethod
-    def forward(ctx, x, conv_w, gamma, beta, running_mean, running_var, eps, momentum, training, backend):
+    def forward(ctx, x, conv_w, gamma, beta, running_mean, running_var, eps, momentum, training, backend, nbt=None):
         first = x.dim() == 4
         g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        cout = conv_w.shape[0]
+        direct = bool(training) and x.is_cuda and _direct_ok(conv_w, gamma, beta) and \
+            (backend in ('auto', 'tcgen05') or first)
+        ctx.direct, ctx.params = direct, (conv_w, gamma, beta)
+        stats_buf = _scratch(conv_w, 'stats', 2 * cout) if direct else None
+
+        def finalize(stats, count):
+            if direct:
+                return bn_finalize2(stats, count, eps, momentum, running_mean, running_var, nbt)
+            if nbt is not None:
+                nbt.add_(1)
+            return bn_finalize(stats, count, eps, momentum, running_mean, running_var)
+
         if first and conv1_fused_enabled():
             shape = tuple(x.shape)
             xp = conv1_pad_input_hd(x)
             if training:
-                stats = conv1_fused_stats(xp, conv_w, shape)
-                mean, invstd = bn_finalize(stats, x.numel(), eps, momentum, running_mean, running_var)
+                mean, invstd = finalize(conv1_fused_stats(xp, conv_w, shape, out=stats_buf), x.numel())
             else:
                 mean, invstd = running_mean.float(), (running_var.float() + eps).rsqrt()
             p, code = conv1_fused_pool(xp, conv_w, mean, invstd, g, b, shape)
@@ -287,13 +345,15 @@ class ConvBnReluPoolFn(_torch.autograd.Function):
         ctx.fused_shape = None
         if first:
             y, stats = conv1_fwd(x, conv_w)
+            if direct:
+                stats_buf.copy_(stats); stats = stats_buf
         else:
-            y, stats = conv3d_fwd(x, conv_w, backend, want_stats=bool(training))
+            y, stats = conv3d_fwd(x, conv_w, backend, want_stats=bool(training), stats_out=stats_buf)
         N, D, H, W, C = y.shape
         if training:
             if stats is None:
-                stats = bn_stats(y)
-            mean, invstd = bn_finalize(stats, N * D * H * W, eps, momentum, running_mean, running_var)
+                stats = bn_stats(y, out=stats_buf)
+            mean, invstd = finalize(stats, N * D * H * W)
         else:
             mean = running_mean.float()
             invstd = (running_var.float() + eps).rsqrt()
@@ -306,14 +366,37 @@ class ConvBnReluPoolFn(_torch.autograd.Function):
     def backward(ctx, dp):
         if not ctx.training:   # eval-mode BN has no batch-statistics terms; not a training path
             raise RuntimeError('ConvBnReluPoolFn.backward is only defined for training-mode BatchNorm')
+        conv_w_p, gamma_p, beta_p = ctx.params
+        cout, cin = conv_w_p.shape[0], conv_w_p.shape[1]
+        direct = ctx.direct and _direct_ok(conv_w_p, gamma_p, beta_p)
+        if direct and not ctx.first:
+            from .conv3d_wgrad import _SUPPORTED
+            direct = (cin, cout) in _SUPPORTED
+        acc = _scratch(conv_w_p, 'acc', 2 * cout) if direct else None
+        none = (None,) * 7
         if ctx.fused_shape is not None:
             xp, conv_w, code, mean, invstd, g, b, p = ctx.saved_tensors
-            dw, dgamma, dbeta = conv1_fused_bwd(xp, conv_w, mean, invstd, g, b, p, code, dp, ctx.fused_shape)
-            return None, dw.to(conv_w.dtype), dgamma.to(g.dtype), dbeta.to(b.dtype), None, None, None, None, None, None
+            dwbuf = _scratch(conv_w_p, 'dw', 27 * cin * cout) if direct else None
+            dw, dgamma, dbeta = conv1_fused_bwd(xp, conv_w, mean, invstd, g, b, p, code, dp, ctx.fused_shape, acc=acc, dw=dwbuf)
+            if direct:
+                conv_block_grad_finalize(dwbuf, acc, conv_w_p, gamma_p, beta_p, cin, cout, transposed=False)
+                return (None, None, None, None) + none
+            return (None, dw.to(conv_w.dtype), dgamma.to(g.dtype), dbeta.to(b.dtype)) + none
         x, conv_w, y, mean, invstd, g, b, p = ctx.saved_tensors
-        dy, dgamma, dbeta = bn_relu_pool_bwd(y, dp.contiguous(), mean, invstd, g, b, p=p)
+        dy, dgamma, dbeta = bn_relu_pool_bwd(y, dp.contiguous(), mean, invstd, g, b, p=p, acc=acc)
         if ctx.first:
             dx, dw = None, conv1_wgrad(dy, x)
+            if direct:                                    # stored-y first block: dW arrives in the parameter layout
+                dwbuf = _scratch(conv_w_p, 'dw', 27 * cin * cout)
+                dwbuf.copy_(dw.reshape(-1))
+                conv_block_grad_finalize(dwbuf, acc, conv_w_p, gamma_p, beta_p, cin, cout, transposed=False)
+                return (None, None, None, None) + none
+        elif direct:
+            from .conv3d import conv3d_igemm_bwd
+            dwbuf = _scratch(conv_w_p, 'dw', 27 * cin * cout)
+            dx, _ = conv3d_igemm_bwd(dy, x, conv_w, need_dx=ctx.needs_input_grad[0], raw_dw=dwbuf.view(27 * cin, cout))
+            conv_block_grad_finalize(dwbuf, acc, conv_w_p, gamma_p, beta_p, cin, cout, transposed=True)
+            return (dx, None, None, None) + none
         else:
             dx, dw = conv3d_bwd(dy, x, conv_w, need_dx=ctx.needs_input_grad[0], backend=ctx.backend)
-        return dx, dw.to(conv_w.dtype), dgamma.to(g.dtype), dbeta.to(b.dtype), None, None, None, None, None, None
+        return (dx, dw.to(conv_w.dtype), dgamma.to(g.dtype), dbeta.to(b.dtype)) + none

@@ -77,6 +77,13 @@ class GraphedStep:
             width = sum(t.numel() for t in _state_tensors(warm['averages'], warm['metrics'])) or 1
             if self.ring is None or self.ring.shape[1] != width:
                 self.ring = _torch.zeros(self.ring_len, width, dtype=_torch.float32, device=self.device)
+        # Drop the warm-up autograd graph BEFORE capturing.  While `warm['loss']` is alive the parameters' AccumulateGrad
+        # nodes created on the warm-up stream are reused by the captured backward; a node that receives no gradient
+        # (kernels that accumulate straight into .grad return None) then makes the engine wait on that un-captured stream
+        # at the end of backward: cudaErrorStreamCaptureIsolation.
+        warm = None
+        import gc
+        gc.collect()
         _torch.cuda.current_stream(self.device).wait_stream(side)
         _torch.cuda.synchronize(self.device)
 

@@ -555,3 +555,36 @@ def test_small_linear_matches_torch_and_accumulates_in_place(dev, M, K, N, relu,
     x2 = x0.clone().requires_grad_(True)
     SmallLinearFn.apply(x2, lin.weight, lin.bias, relu).backward(g)
     assert torch.allclose(lin.weight.grad, gw, rtol=2e-3, atol=2e-4) and torch.allclose(lin.bias.grad, gb, rtol=2e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize('first', [True, False])
+def test_conv_block_direct_grad_mode_matches_autograd_mode(dev, first):
+    """parameters that already own .grad buffers -> persistent accumulators + one finalize launch, None to autograd;
+    must give the same gradients (added onto what .grad held) and the same running statistics as the plain mode."""
+    from coinstac_dinunet_b200.ops import vbm
+    torch.manual_seed(21)
+    cin, cout = (1, 16) if first else (16, 32)
+    x = torch.randn(2, 8, 10, 12, device=dev) if first else torch.randn(2, 8, 10, 12, cin, device=dev).bfloat16()
+    w0 = torch.randn(cout, cin, 3, 3, 3, device=dev) * 0.1
+    g0, b0 = torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev) * 0.1
+    dp = None
+    out = {}
+    for mode in ('plain', 'direct', 'direct'):                  # direct twice: the accumulators must come back zeroed
+        w, g, b = (t.clone().requires_grad_(True) for t in (w0, g0, b0))
+        rm, rv, nbt = torch.zeros(cout, device=dev), torch.ones(cout, device=dev), torch.zeros((), dtype=torch.long, device=dev)
+        if mode == 'direct':
+            w.grad, g.grad, b.grad = torch.full_like(w, 0.25), torch.full_like(g, 0.25), torch.full_like(b, 0.25)
+        xin = x.clone().requires_grad_(not first)
+        p = vbm.ConvBnReluPoolFn.apply(xin, w, g, b, rm, rv, 1e-5, 0.1, True, 'auto', nbt)
+        dp = torch.randn_like(p) if dp is None else dp
+        p.backward(dp)
+        off = 0.25 if mode == 'direct' else 0.0
+        cur = {'p': p.detach().float(), 'dw': w.grad - off, 'dg': g.grad - off, 'db': b.grad - off, 'rm': rm, 'rv': rv,
+               'dx': None if first else xin.grad.float()}
+        assert int(nbt) == 1
+        if out:
+            for k, v in cur.items():
+                if v is not None:
+                    assert torch.allclose(v, out[k], rtol=2e-3, atol=2e-3), (mode, k, float((v - out[k]).abs().max()))
+        else:
+            out = cur
