@@ -92,13 +92,16 @@ class LinearFn(_torch.autograd.Function):
         return dx, dw, db, None
 
 
+DIRECT_GRAD_DISABLED = False      # set by DistArena.enable_overlap(): bucket launches are driven by post-accumulate-grad hooks
+
+
 def direct_grad_ok(param):
     """True when a backward kernel may accumulate straight into ``param.grad`` (fp32, contiguous, already allocated -
     e.g. a view of the DistArena gradient arena) and return ``None`` to autograd: no temporary, no AccumulateGrad add.
     COINN_DIRECT_GRAD=0 disables it (needed if post-accumulate-grad hooks must fire for every parameter)."""
     import os
     g = getattr(param, 'grad', None)
-    return (os.environ.get('COINN_DIRECT_GRAD', '1') != '0' and g is not None and param.dtype == _torch.float32
+    return (not DIRECT_GRAD_DISABLED and os.environ.get('COINN_DIRECT_GRAD', '1') != '0' and g is not None and param.dtype == _torch.float32
             and g.dtype == _torch.float32 and g.is_contiguous() and param.is_contiguous())
 
 

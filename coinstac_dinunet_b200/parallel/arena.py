@@ -272,6 +272,8 @@ class DistArena:
         is left and joins the streams.  Only meaningful for the ``nvlink`` backend."""
         if self.backend != 'nvlink' or getattr(self, '_overlap', None):
             return self
+        from ..ops import linear as _lin
+        _lin.DIRECT_GRAD_DISABLED = True    # gradients must pass through AccumulateGrad so that the hooks below fire
         cap = max(int(bucket_bytes) // 4, 4 * max(self.world, 1))
         buckets, start, members = [], 0, []
         for i, (p, off) in enumerate(zip(self.params, self.offsets)):
