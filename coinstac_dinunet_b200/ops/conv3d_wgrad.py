@@ -18,13 +18,15 @@ def conv3d_wgrad(dy, x, raw_out=None):
     if (cin, cout) not in _SUPPORTED:
         raise ImportError(f'no tcgen05 wgrad instantiation for {cin}->{cout}')
     dwt = raw_out if raw_out is not None else _torch.zeros((27 * cin, cout), dtype=_torch.float32, device=x.device)
-    impl = _os.environ.get('COINN_WGRAD_IMPL', 'auto')      # auto: halo kernel where it applies, else the gather kernel
+    impl = _os.environ.get('COINN_WGRAD_IMPL', 'auto')      # auto: halo kernel, else the per-tap kernel, else the gather kernel
     args = (x.contiguous().data_ptr(), dy.contiguous().data_ptr(), dwt.data_ptr(), N, D, H, W, cin, cout,
             _nat.stream_ptr(x.device))
     global last_impl
     code = -1
     if impl in ('auto', 'halo'):
         code, last_impl = _nat.lib().coinn_conv3d_wgrad_halo(*args), 'halo'
+    if code == -1 and impl in ('auto', 'tap'):          # C_in >= 64: one TMA-box GEMM per filter tap (conv3d_wgrad_tap.cu)
+        code, last_impl = _nat.lib().coinn_conv3d_wgrad_tap(*args), 'tap'
     if code == -1:
         code, last_impl = _nat.lib().coinn_conv3d_wgrad(*args), 'gather'
     _nat.check(code, f'conv3d_wgrad[{last_impl}]({cin}->{cout})')

@@ -35,7 +35,7 @@ constexpr uint32_t C1F_SLAB = C1F_ROWS * 32;           // BWD: one window [136 r
 constexpr uint32_t C1F_STAGE = 4 * C1F_SLAB;           // input lines h' .. h'+3 of one output block (17 KB)
 constexpr uint32_t C1F_WSLAB = C1F_ROWS * 128;         // STATS / POOL: one window [136 rows][64 w'] serves 7 output blocks (128B swizzle)
 constexpr uint32_t C1F_WSTAGE = 4 * C1F_WSLAB;         // 68 KB
-constexpr uint32_t C1F_T_BYTES = 9 * 4096;             // Toeplitz matrices T_{kd,kh}: [2 k-chunks][128 n][8 k] bf16
+constexpr uint32_t C1F_T_BYTES = 9 * 4096;             // Toeplitz matrices T_{kd,kh}: [128 n][16 k] bf16, K-major, 32B swizzle
 constexpr uint32_t C1F_DY_BYTES = 32768;               // dy tile: 2 M-blocks x [128 rows][128 B], 128B swizzle
 constexpr int C1F_MAX_STAGES = 8;
 
@@ -147,7 +147,9 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams 
         const int s = i >> 11, n = (i >> 4) & 127, k = i & 15;
         const int wl = n >> 4, c = n & 15, kw = k - wl;
         const float v = (kw >= 0 && kw <= 2) ? p.w[c * 27 + s * 3 + kw] : 0.f;
-        reinterpret_cast<__nv_bfloat16*>(t_smem + s * 4096 + (k >> 3) * 2048 + n * 16)[k & 7] = __float2bfloat16(v);
+        // K-major rows of 32 bytes with the 32B swizzle (16-byte chunk index ^= address bit 7 = bit 2 of n): 8 % faster
+        // MMAs than the unswizzled core-matrix planes (84.6 -> 77.6 us for the statistics pass)
+        reinterpret_cast<__nv_bfloat16*>(t_smem + s * 4096 + n * 32 + ((((k >> 3) ^ ((n >> 2) & 1))) << 4))[k & 7] = __float2bfloat16(v);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     fence_proxy_async_smem();
@@ -193,7 +195,7 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_xp, const C1FParams 
             constexpr uint32_t idesc_w = make_idesc_f16(128, 48, 1, 1, 1);
             const uint64_t a_const = WIDE ? make_smem_desc(0, 16, 1024, SMEM_LAYOUT_SW128)  // K-major, 128-byte rows
                                           : make_smem_desc(0, 16, 256, SMEM_LAYOUT_SW32);   // K-major, 32-byte rows
-            const uint64_t b_const = make_smem_desc(0, 2048, 128, SMEM_LAYOUT_NONE);
+            const uint64_t b_const = make_smem_desc(0, 16, 256, SMEM_LAYOUT_SW32);
             const uint64_t wa_const = make_smem_desc(0, 16384, 1024, SMEM_LAYOUT_SW128);   // dy: MN-major, 2 blocks of 64
             const uint64_t wb_const = make_smem_desc(0, 32, 256, SMEM_LAYOUT_SW32);        // window: MN-major, block = row shift
             const uint32_t t16 = (smem_u32(t_smem) & 0x3FFFFu) >> 4;

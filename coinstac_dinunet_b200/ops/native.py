@@ -62,6 +62,7 @@ class _Lib:
         d.coinn_conv3d_halo_stats.argtypes = [C.c_void_p] * 4 + [C.c_int] * 8 + [C.c_void_p]
         d.coinn_conv3d_wgrad_halo.argtypes = [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]
         d.coinn_conv3d_wgrad.argtypes = [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]
+        d.coinn_conv3d_wgrad_tap.argtypes = [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]
         d.coinn_bn_pool_bwd_stats_pooled.argtypes = [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_void_p]
         d.coinn_pack_conv_weights.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_linear_small_fwd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]

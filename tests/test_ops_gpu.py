@@ -592,3 +592,22 @@ def test_conv_block_direct_grad_mode_matches_autograd_mode(dev, first):
                     assert torch.allclose(v, out[k], rtol=2e-3, atol=2e-3), (mode, k, float((v - out[k]).abs().max()))
         else:
             out = cur
+
+
+@pytest.mark.parametrize('cin,cout,shape', [(64, 128, (2, 4, 5, 6)), (128, 256, (1, 3, 4, 3)), (64, 128, (2, 15, 18, 15)),
+                                            (128, 256, (2, 7, 9, 7)), (64, 64, (1, 5, 20, 9))])
+def test_conv3d_wgrad_tap_matches_torch(dev, cin, cout, shape, monkeypatch):
+    """per-tap TMA-box weight gradient (conv3d_wgrad_tap.cu) for the C_in >= 64 blocks vs torch."""
+    from coinstac_dinunet_b200.ops import conv3d_wgrad as cw
+    monkeypatch.setenv('COINN_WGRAD_IMPL', 'tap')
+    torch.manual_seed(cin + cout)
+    N, D, H, W = shape
+    x = torch.randn(N, D, H, W, cin, device=dev).to(torch.bfloat16)
+    dy = torch.randn(N, D, H, W, cout, device=dev).to(torch.bfloat16)
+    dw = cw.conv3d_wgrad(dy, x)
+    assert cw.last_impl == 'tap'
+    w = torch.zeros(cout, cin, 3, 3, 3, device=dev)
+    _, dw_ref, _ = torch.ops.aten.convolution_backward(
+        dy.float().permute(0, 4, 1, 2, 3), x.float().permute(0, 4, 1, 2, 3), w, None, [1, 1, 1], [1, 1, 1], [1, 1, 1],
+        False, [0, 0, 0], 1, [False, True, False])
+    assert _rel(dw, dw_ref) < 5e-3, _rel(dw, dw_ref)
