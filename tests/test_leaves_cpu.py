@@ -224,3 +224,17 @@ def test_imageutils_and_plotter(tmp_path):
     cache = {'log_header': 'Loss|Accuracy,F1', 'train_log': [[1.0, .5, .4], [.8, .6, .5], [.6, .7, .6]]}
     plotter.plot_progress(cache, str(tmp_path), plot_keys=['train_log'])
     assert any(f.startswith('train_log_0') for f in os.listdir(tmp_path))
+
+
+def test_bench_stdout_carries_only_the_json_line():
+    """bench.py contract: ONE JSON line on stdout.  Library banners (NCCL prints its version on the first communicator)
+    and stray prints must end up on stderr."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, bench; bench._guard_stdout(); print('python noise'); os.system('echo c-level noise'); "
+            "bench.emit({'metric': 'm', 'value': 1.5})")
+    r = subprocess.run([sys.executable, '-c', code], cwd=root, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1 and json.loads(lines[0]) == {'metric': 'm', 'value': 1.5}
+    assert 'python noise' in r.stderr and 'c-level noise' in r.stderr
