@@ -1,14 +1,22 @@
-"""Fused blocks of the VBM 3-D CNN on the hand-written kernels (``csrc/vbm_fused.cu`` +
-``csrc/conv3d_tcgen05.cu``).  Activations are channels-last ``[N, D, H, W, C]`` bf16.
+"""Fused blocks of the VBM 3-D CNN on the hand-written kernels (``csrc/conv1_fused.cu``, ``csrc/conv3d_halo.cu``,
+``csrc/conv3d_wgrad_*.cu``, ``csrc/conv3d_tma.cu``, ``csrc/vbm_fused.cu``).  Activations are channels-last
+``[N, D, H, W, C]`` bf16.
 
-One ``ConvBnReluPool`` block = Conv3d(k3, p1, no bias) -> BatchNorm3d (batch statistics) -> ReLU ->
-MaxPool3d(2).  Passes over HBM per block:
+One ``ConvBnReluPool`` block = Conv3d(k3, p1, no bias) -> BatchNorm3d (batch statistics) -> ReLU -> MaxPool3d(2).
 
-    forward   conv (writes y)  ->  stats (reads y; fused into conv1)  ->  bn+relu+pool (reads y, writes y/8)
-    backward  pass A (reads y, dp -> dgamma, dbeta)  ->  pass B (reads y, dp, writes dy)  ->  dgrad + wgrad
+Blocks 2-5 (stored conv output y):
 
-versus conv, BN-stat, BN-apply, ReLU, pool (each a full read+write) in the PyTorch chain - whose
-channels-last-3d BatchNorm backward alone takes 40 ms per step on a B200 (profiles/r1_launches_torch.txt).
+    forward   conv (writes y; the halo kernel also emits the BatchNorm sums)  ->  bn+relu+pool (reads y, writes y/8)
+    backward  pooled sums (reads p, dp -> dgamma, dbeta)  ->  apply (reads y, dp, writes dy)  ->  dgrad + wgrad
+              ->  grad finalize (raw dW, dgamma, dbeta folded into .grad, accumulators re-zeroed)
+
+Block 1 (C_in = 1, 543 MB of y at the benchmark shape) stores nothing at full resolution: the banded-Toeplitz tcgen05
+convolution is recomputed in a statistics pass, a BN+ReLU+pool pass (pooled output + one arg-max code byte per value)
+and the backward pass, where the gradient tile goes from registers to shared memory and straight into the weight-gradient
+MMAs (``conv1_fused_*`` below; COINN_CONV1_FUSED=0 selects the stored-y kernels instead).
+
+For comparison the PyTorch chain is conv, BN-stat, BN-apply, ReLU, pool - each a full read+write - and its
+channels-last-3d BatchNorm backward alone takes 40 ms per step on a B200 (profiles/r1_launches_torchmodules.txt).
 """
 import ctypes as _C
 import os as _os
