@@ -238,3 +238,24 @@ def test_bench_stdout_carries_only_the_json_line():
     lines = r.stdout.splitlines()
     assert len(lines) == 1 and json.loads(lines[0]) == {'metric': 'm', 'value': 1.5}
     assert 'python noise' in r.stderr and 'c-level noise' in r.stderr
+
+
+def test_native_library_exports_every_declared_symbol():
+    """``ops/native.py`` declares ctypes signatures for the kernels' C entry points; after ``__graft_entry__.build()`` the
+    in-tree ``_b200_ops.so`` must export all of them (it is loaded lazily, so a missing symbol would otherwise only
+    surface on a GPU box)."""
+    import ctypes, os, re
+    import pytest
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(here, 'coinstac_dinunet_b200', 'ops', '_b200_ops.so')
+    if not os.path.exists(so):
+        pytest.skip('kernel library not built (run __graft_entry__.build())')
+    try:
+        lib = ctypes.CDLL(so)
+    except OSError as exc:                                   # no CUDA runtime on this machine
+        pytest.skip(f'cannot load {so}: {exc}')
+    src = open(os.path.join(here, 'coinstac_dinunet_b200', 'ops', 'native.py')).read()
+    names = sorted(set(re.findall(r'd\\.(coinn_\\w+)\\.', src)))
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
