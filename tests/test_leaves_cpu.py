@@ -255,7 +255,7 @@ def test_native_library_exports_every_declared_symbol():
     except OSError as exc:                                   # no CUDA runtime on this machine
         pytest.skip(f'cannot load {so}: {exc}')
     src = open(os.path.join(here, 'coinstac_dinunet_b200', 'ops', 'native.py')).read()
-    names = sorted(set(re.findall(r'd\\.(coinn_\\w+)\\.', src)))
+    names = sorted(set(re.findall(r'd\.(coinn_\w+)\.', src)))
     assert len(names) >= 30
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
