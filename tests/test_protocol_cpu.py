@@ -72,3 +72,25 @@ def test_training_learns(fs_sites):
     rows = open(os.path.join(eng.remote_state['outputDirectory'], 'fsv', 'global_test_metrics.csv')).read().split('\n')
     loss, acc, f1 = (float(v) for v in rows[1].split(',')[:3])
     assert acc > 0.7, rows
+
+
+def test_half_precision_wire_format(fs_sites):
+    """``precision_bits=16`` (reference local.py:54, learner.py:17): gradients travel as float16 object arrays; the
+    replicas still end bit-identical because both sites apply the same averaged float16 gradient."""
+    from coinstac_dinunet_b200.utils import tensorutils
+    seen = []
+    orig = tensorutils.save_arrays
+
+    def spy(path, arrays):
+        seen.append({str(np.asarray(a).dtype) for a in arrays})
+        return orig(path, arrays)
+    tensorutils.save_arrays = spy
+    try:
+        eng = fs_sites(spec={'num_folds': None, 'split_ratio': [0.6, 0.2, 0.2], 'epochs': 1, 'precision_bits': 16})
+        eng.run_nodes(FSVTrainer, FSVDataset, max_rounds=500)
+    finally:
+        tensorutils.save_arrays = orig
+    assert eng.trace[-2]['remote'] == 'success'
+    assert seen and all(d == {'float16'} for d in seen), seen[:3]
+    a, b = (_params(eng.site_cache[s]) for s in eng.site_ids)
+    assert torch.equal(a, b)
