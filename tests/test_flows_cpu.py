@@ -103,3 +103,38 @@ def test_example_computations_run_in_the_simulator():
     eng = sim.main('fsv')
     assert eng.trace[-2]['remote'] == 'success'
     assert json.load(open(os.path.join(root, 'examples', 'vbm', 'compspec.json')))['computation']['input']['transport']['default'] == 'nvlink'
+
+
+def test_gradient_accumulation_and_early_stop(fs_sites):
+    """``local_iterations=2`` (micro-batches accumulate before every reduce, reference learner.py:32-47) and
+    ``patience=1`` (remote early stop, remote.py:286-287) through the whole protocol."""
+    eng = fs_sites(spec={'num_folds': None, 'split_ratio': [0.6, 0.2, 0.2], 'epochs': 30, 'patience': 1,
+                         'local_iterations': 2, 'learning_rate': 1e-6})          # lr ~ 0: validation score cannot improve
+    rounds = eng.run_nodes(FSVTrainer, FSVDataset, max_rounds=3000)
+    assert eng.trace[-2]['remote'] == 'success'
+    # 30 epochs of 15 / 11 samples at batch 4 x 2 micro-batches would need > 100 reduce rounds; patience stops long before
+    assert rounds < 60, rounds
+    a, b = (torch.cat([p.detach().reshape(-1) for p in eng.site_cache[s]['nn']['fs_net'].parameters()]) for s in eng.site_ids)
+    assert torch.equal(a, b)
+
+
+def test_multiclass_protocol_uses_confusion_matrix(tmp_path):
+    """num_class = 3 -> ConfusionMatrix metrics on the sites and their (fixed) aggregation on the remote."""
+    import csv
+    from coinstac_dinunet_b200.engine import InProcessEngine
+    from coinstac_dinunet_b200.models import write_synthetic_site
+    spec = dict(task_id='fsv', mode='train', data_dir='data', labels_file='labels.json', input_size=66, num_class=3,
+                batch_size=4, epochs=2, num_folds=None, split_ratio=[0.6, 0.2, 0.2], learning_rate=1e-2, seed=3,
+                monitor_metric='f1', metric_direction='maximize', log_header='Loss|Accuracy,F1', verbose=False)
+    eng = InProcessEngine(tmp_path / 'work', n_sites=2, inputspec=spec)
+    for i, site in enumerate(eng.site_ids):
+        write_synthetic_site(eng.site_state[site]['baseDirectory'], 30, (66,), num_class=3, seed=i)
+    eng.run_nodes(FSVTrainer, FSVDataset, max_rounds=1000)
+    assert eng.trace[-2]['remote'] == 'success'
+    from coinstac_dinunet_b200.metrics import ConfusionMatrix
+    from coinstac_dinunet_b200.distrib.nodes.remote import EmptyDataHandle
+    tr = FSVTrainer(data_handle=EmptyDataHandle(eng.site_cache['local0'], {}, eng.site_state['local0']))
+    assert isinstance(tr.new_metrics(), ConfusionMatrix)
+    path = os.path.join(eng.remote_state['outputDirectory'], 'fsv', 'global_test_metrics.csv')
+    rows = list(csv.reader(open(path)))
+    assert len(rows) >= 2 and all(0.0 <= float(v) <= 1.0 for v in rows[-1][1:] if v not in ('', 'nan'))
