@@ -3,6 +3,8 @@
 
     python bench.py --gpus N --steps K --warmup W            # our engine
     python bench.py --impl reference --gpus N ...             # unmodified reference (baseline/_ref)
+    python bench.py --impl nccl_cudnn --gpus N ...            # R1: same nn.Module on cuDNN/cuBLAS bf16 + NCCL + fused Adam
+    python bench.py --model fs ...                            # BASELINE config 2 (FreeSurfer MLP) instead of the VBM CNN
 
 N > 1 is launched by ``python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N``:
 one rank per GPU == one federated site per GPU.  Both arms train the same architecture
@@ -14,8 +16,11 @@ Our arm goes through the public API the whole way: ``DistEngine`` drives ``COINN
 (forward/backward + fused cross-GPU reduce + Adam in one kernel).  Two measurements:
   * ``value``  - K steps, device-timed (CUDA events, max over ranks), inputs resident on the device
                  (4+ rotating batches, working set >> L2);
-  * ``e2e``    - the same K steps where every step copies its batch from pinned host memory
-                 (H2D) and reads the step's loss back (D2H).
+  * ``e2e``    - the same K steps where every step copies its batch (fp32 volumes, the dtype the
+                 reference arm moves) from pinned host memory (H2D) and reads the step's loss back
+                 (D2H); ``e2e_bf16_host`` repeats it with the volumes stored as bf16 on the host.
+``vs_baseline`` = value / the R1 number measured on this hardware for the same N
+(``baseline/r1_measured.json``, written from ``--impl nccl_cudnn`` runs).
 The line printed by rank 0 follows the driver's contract.
 """
 import argparse
@@ -39,71 +44,104 @@ def parse():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=10)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'nccl_cudnn'])
     ap.add_argument('--model', default='vbm', choices=['vbm', 'fs'])
     ap.add_argument('--batch', type=int, default=None, help='per-site batch (default 8 vbm / 16 fs)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--transport', default='nvlink', choices=['nvlink', 'nccl'])
     ap.add_argument('--variant', default='auto', choices=['auto', 'one_shot', 'two_shot', 'nvls'])
-    ap.add_argument('--overlap', type=int, default=0, help='bucketed reduce+update launched from grad hooks during backward')
+    ap.add_argument('--overlap', type=int, default=-1,
+                    help='bucketed reduce+update launched during backward (-1: on when --gpus > 1)')
+    ap.add_argument('--bucket-mb', type=float, default=4.0)
+    ap.add_argument('--layout', default='auto', choices=['auto', 'contiguous', 'channels_last_3d'], help='R1 arm only')
     ap.add_argument('--native', type=int, default=1, help='use the hand-written sm_100a model kernels')
     ap.add_argument('--skip-e2e', action='store_true')
-    ap.add_argument('--input-dtype', default='bf16', choices=['bf16', 'fp32'],
-                    help='dtype of the volumes in pinned host memory (bf16 halves the PCIe bytes; compute is bf16 anyway)')
+    ap.add_argument('--input-dtype', default='fp32', choices=['bf16', 'fp32'],
+                    help='dtype of the volumes in pinned host memory for the headline e2e number (fp32 = what the '
+                         'reference arm moves; the bf16-host variant is reported next to it as e2e_bf16_host)')
     ap.add_argument('--graph', type=int, default=1, help='capture the whole step in a CUDA graph')
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """`nvidia-smi` clocks + throttle reasons sampled every 25 ms during the timed region."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
-         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock + throttle reasons of one GPU, sampled every ~2 ms by an NVML thread while a timed region runs
+    (a timed region of 20 steps is ~40 ms: an `nvidia-smi -lms` child cannot resolve that).  Falls back to one
+    `nvidia-smi` query when NVML is not importable."""
+    REASONS = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40}
 
     def __init__(self, index):
-        self.index, self.proc, self.path = index, None, None
+        self.index, self.thread, self.stop_flag = index, None, False
+        self.sm, self.mask, self.max_mhz, self.power = [], 0, None, []
+        self.h = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(index)
+            bus = f'{getattr(pr, "pci_domain_id", 0):08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0'
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+            getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons', None)
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                if reasons is not None:
+                    self.mask |= int(reasons(self.h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            fd, self.path = tempfile.mkstemp(suffix='.csv')
-            os.close(fd)
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.index), '-lms', '25'],
-                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        self.sm, self.mask, self.power, self.stop_flag = [], 0, [], False
+        if self.h is not None:
+            import threading
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
 
     def stop(self):
-        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        if self.proc is None:
+        out = {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': [], 'samples': 0}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            self.thread = None
+        if self.sm:
+            out.update(sm_mhz=statistics.median(self.sm), samples=len(self.sm),
+                       power_w_max=max(self.power) if self.power else None)
+            out['reasons'] = sorted(k for k, bit in self.REASONS.items() if self.mask & bit)
             return out
-        try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
+        try:    # fall-back: one query (after the region; better than nothing)
+            q = 'clocks.sm,clocks.max.sm'
+            r = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                               capture_output=True, text=True, timeout=10).stdout.split(',')
+            out.update(sm_mhz=float(r[0]), sm_max_mhz=float(r[1]), samples=1)
         except Exception:
             pass
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        try:
-            for line in open(self.path):
-                f = [x.strip() for x in line.split(',')]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
-                except ValueError:
-                    continue
-                for name, val in zip(names, f[5:9]):
-                    if val.lower().startswith('active'):
-                        reasons.add(name)
-            os.remove(self.path)
-        except Exception:
-            pass
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
-        out['reasons'] = sorted(reasons)
         return out
+
+
+def merge_clocks(*parts):
+    """One `clocks` record from the samplers of several timed regions (device-timed + end-to-end)."""
+    sm = [p['sm_mhz'] for p in parts if p and p.get('sm_mhz')]
+    out = {'sm_mhz': statistics.median(sm) if sm else None,
+           'sm_max_mhz': max([p['sm_max_mhz'] for p in parts if p and p.get('sm_max_mhz')] or [None]),
+           'reasons': sorted({r for p in parts if p for r in p.get('reasons', [])}),
+           'samples': sum(p.get('samples', 0) for p in parts if p)}
+    pw = [p.get('power_w_max') for p in parts if p and p.get('power_w_max')]
+    if pw:
+        out['power_w_max'] = max(pw)
+    return out
 
 
 def dist_setup(n):
@@ -116,34 +154,66 @@ def dist_setup(n):
     os.environ.setdefault('WORLD_SIZE', '1')
     local = int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
+    import importlib.util    # by path: the reference arm must not import our package
+    spec = importlib.util.spec_from_file_location('_coinn_affinity', os.path.join(ROOT, 'coinstac_dinunet_b200', 'utils', 'affinity.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    aff = mod.pin_to_gpu(local, ranks_per_node=max(1, (n + 1) // 2))      # NUMA-local CPUs + pinned buffers, sane thread pool
     if not dist.is_initialized():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     assert dist.get_world_size() == n, f'--gpus {n} but WORLD_SIZE={dist.get_world_size()} (launch with torchrun)'
-    return dist.get_rank(), local
+    return dist.get_rank(), local, aff
 
 
 def timed(fn, dist, torch):
     """barrier + sync | events around fn | sync + barrier; returns max-over-ranks milliseconds."""
-    dist.barrier(device_ids=[torch.cuda.current_device()])
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    result = fn()
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier(device_ids=[torch.cuda.current_device()])
+    import gc
+    gc.collect()
+    gc.disable()                     # a generation-2 collection inside a 40 ms region is a 10 % outlier
+    try:
+        dist.barrier(device_ids=[torch.cuda.current_device()])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        result = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier(device_ids=[torch.cuda.current_device()])
+    finally:
+        gc.enable()
     ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms.item()), result
+
+
+def r1_number(model, n):
+    """samples/s of the R1 arm (cuDNN bf16 + NCCL + fused Adam, CUDA graph) recorded for this model at N GPUs."""
+    try:
+        with open(os.path.join(ROOT, 'baseline', 'r1_measured.json')) as fp:
+            return float(json.load(fp)[model][str(n)]['value'])
+    except Exception:
+        return None
+
+
+def metric_name(model):
+    return 'samples/sec (whole box, max over sites) VBM-3D-CNN dSGD' if model == 'vbm' \
+        else 'samples/sec (whole box, max over sites) FreeSurfer-MLP dSGD'
+
+
+def gap_stats(stamps):
+    """Host-side inter-step gaps (ms) of an end-to-end region: shows whether the host ever starved the device."""
+    if not stamps or len(stamps) < 3:
+        return None
+    gaps = sorted((b - a) * 1e3 for a, b in zip(stamps[:-1], stamps[1:]))
+    return {'p50': round(gaps[len(gaps) // 2], 3), 'max': round(gaps[-1], 3)}
 
 
 # ------------------------------------------------------------------------------------- ours
 def run_ours(a):
     import torch
     import torch.distributed as dist
-    rank, local = dist_setup(a.gpus)
+    rank, local, aff = dist_setup(a.gpus)
     from coinstac_dinunet_b200 import ops
-    from coinstac_dinunet_b200.config.keys import Phase
     from coinstac_dinunet_b200.engine import DistEngine
     from coinstac_dinunet_b200.models import FSVTrainer, InMemorySynthetic, VBMTrainer
     from coinstac_dinunet_b200.models.common import pinned_collate
@@ -153,11 +223,13 @@ def run_ours(a):
     trainer_cls = VBMTrainer if a.model == 'vbm' else FSVTrainer
     n_distinct = 4 * batch                                   # 4 rotating batches: 272 MB fp32 for VBM (> L2)
     n_files = batch * (a.warmup + a.steps + 4) * 2
+    overlap = (a.gpus > 1) if a.overlap < 0 else bool(a.overlap)
+    host_dt = {'fp32': torch.float32, 'bf16': torch.bfloat16}
 
     class Volumes(InMemorySynthetic):
         def __init__(self, **kw):
             super().__init__(shape=shape, num_class=2, seed=100 + rank, pin=True,
-                             dtype=torch.bfloat16 if (a.input_dtype == 'bf16' and a.model == 'vbm') else torch.float32, **kw)
+                             dtype=host_dt[a.input_dtype] if a.model == 'vbm' else torch.float32, **kw)
 
     work = tempfile.mkdtemp(prefix='coinn_bench_') if rank == 0 else None
     box = [work]
@@ -168,6 +240,7 @@ def run_ours(a):
                 monitor_metric='f1', learning_rate=1e-3, validation_epochs=10 ** 9, transport=a.transport, reduce_variant=a.variant,
                 compute_dtype=a.dtype, channels_last='3d' if a.model == 'vbm' else None, native_ops=bool(a.native),
                 input_shape=list(shape), input_size=shape[0], synthetic_distinct=n_distinct,
+                overlap_backward=overlap, bucket_bytes=int(a.bucket_mb * (1 << 20)), prefetch_depth=3,
                 reference_order=True, pin_memory=False, collate_fn=pinned_collate, cuda_graph=bool(a.graph))
     eng = DistEngine(work, inputspec=spec)
     data_dir = os.path.join(eng.state['baseDirectory'], 'data')
@@ -191,15 +264,17 @@ def run_ours(a):
             break
     assert '_arena' in eng.cache, 'engine never reached the training phase'
 
-    def rounds(k, resident, readback):
+    def rounds(k, resident, readback, dtype=None):
         eng.cache['steps_per_round'] = k
         eng.cache['readback_per_step'] = readback
         eng.cache['synthetic_device'] = f'cuda:{local}' if resident else None
-        # end-to-end mode: stage batch t+1 on a copy stream while step t computes (public dataloader option)
+        # end-to-end mode: stage the next batches on a copy stream while the current step computes (public dataloader option)
         eng.cache['prefetch_to_device'] = None if resident else f'cuda:{local}'
         ds = eng.cache['dataset'].get('train')
-        if ds is not None and (ds._x is None or (ds._x.is_cuda != resident)):
-            ds._x = None                                     # re-materialise on the requested side
+        if ds is not None:
+            want = host_dt[dtype] if (dtype and a.model == 'vbm') else ds.dtype
+            if ds._x is None or ds._x.is_cuda != resident or ds.dtype != want:
+                ds.dtype, ds._x = want, None                 # re-materialise on the requested side / in the requested dtype
         eng.cache['cursor'] = 0                               # fresh iterator over the (re)placed data
         # validation_epochs is huge in the spec, so the aggregator answers every finished round
         # ("epoch") with mode=train and the next round trains again
@@ -212,38 +287,147 @@ def run_ours(a):
     l0 = ops.launch_count
     sampler.start()
     ms, _ = timed(lambda: rounds(a.steps, True, False), dist, torch)
-    clocks = sampler.stop()
+    clocks = [sampler.stop()]
     launches = ops.launch_count - l0
 
     # ---- end to end: pinned host -> device every step, loss read back every step ----
-    e2e = None
-    if not a.skip_e2e:
-        rounds(max(a.warmup, 3), False, True)
-        ms_e2e, _ = timed(lambda: rounds(a.steps, False, True), dist, torch)
-        item = 2 if (a.input_dtype == 'bf16' and a.model == 'vbm') else 4
+    def e2e_run(dtype):
+        rounds(3, False, True, dtype)                         # (re)materialise the pinned pool, allocate staging buffers
+        rounds(max(a.warmup, 3), False, True, dtype)          # W untimed steps in exactly the timed configuration
+        eng.cache['_host_stamps'] = stamps = []
+        sampler.start()
+        ms_e, _ = timed(lambda: rounds(a.steps, False, True, dtype), dist, torch)
+        clocks.append(sampler.stop())
+        eng.cache.pop('_host_stamps', None)
+        item = 2 if (dtype == 'bf16' and a.model == 'vbm') else 4
         h2d = batch * (int(torch.tensor(shape).prod()) * item + 8)
-        e2e = {'value': a.gpus * batch * a.steps / (ms_e2e / 1e3), 'unit': 'samples/s',
-               'ms_per_step': ms_e2e / a.steps, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4}
+        return {'value': a.gpus * batch * a.steps / (ms_e / 1e3), 'unit': 'samples/s', 'ms_per_step': ms_e / a.steps,
+                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'host_input_dtype': dtype if a.model == 'vbm' else 'fp32',
+                'losses_read_back': int(eng.cache.get('losses_read', 0)), 'host_step_gap_ms': gap_stats(stamps)}
+
+    e2e = e2e_alt = None
+    if not a.skip_e2e:
+        e2e = e2e_run(a.input_dtype)
+        if a.model == 'vbm':
+            e2e_alt = e2e_run('bf16' if a.input_dtype == 'fp32' else 'fp32')
 
     arena = eng.cache['_arena']
     if rank == 0:
         value = a.gpus * batch * a.steps / (ms / 1e3)
+        r1 = r1_number(a.model, a.gpus)
+        ov = getattr(arena, '_overlap', None)
         line = {
-            'metric': 'samples/sec (whole box, max over sites) VBM-3D-CNN dSGD' if a.model == 'vbm'
-            else 'samples/sec (whole box, max over sites) FreeSurfer-MLP dSGD',
+            'metric': metric_name(a.model),
             'value': value, 'unit': 'samples/s', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
-            'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': (value / r1) if r1 else None,
             'dtype': a.dtype, 'data': 'synthetic', 'impl': 'ours',
             'config': {'model': 'VBMNet 5x[Conv3d-BN-ReLU-MaxPool] + 3 FC, 3.55M params' if a.model == 'vbm'
                        else 'FSNet MLP 66-256-128-64-32-2',
                        'input': list(shape), 'per_site_batch': batch, 'global_batch': batch * a.gpus,
                        'parallelism': f'dSGD sites={a.gpus} (1 site/GPU)', 'optimizer': 'Adam(1e-3)',
-                       'transport': arena.backend, 'reduce_variant': arena._pick_variant(arena.numel * 4), 'overlap_backward': bool(a.overlap),
+                       'transport': arena.backend,
+                       'reduce_variant': [arena._pick_variant(n * 4) for _, n in arena._launch_units()],
+                       'overlap_backward': bool(ov), 'reduce_buckets': len(ov['buckets']) if ov else 1,
                        'native_model_kernels': bool(a.native), 'cuda_graph': bool(a.graph),
                        'host_input_dtype': a.input_dtype if a.model == 'vbm' else 'fp32',
-                       'l2_policy': 'inputs rotate over 4 distinct batches; activations per step >> 126 MB L2'},
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
+                       'baseline_for_vs_baseline': 'R1 = same nn.Module, cuDNN/cuBLAS bf16 autocast + NCCL all_reduce(AVG) + '
+                                                   'Adam(fused) in one CUDA graph, measured on B200 (baseline/r1_measured.json)',
+                       'l2_policy': 'inputs rotate over 4 distinct batches; activations per step >> 126 MB L2',
+                       'affinity': aff},
+            'clocks': merge_clocks(*clocks), 'e2e': e2e, 'gpu_launches': launches,
         }
+        if e2e_alt is not None:
+            line['e2e_bf16_host' if a.input_dtype == 'fp32' else 'e2e_fp32_host'] = e2e_alt
+        emit(line)
+    dist.barrier(device_ids=[local])
+    dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------- R1
+class _HostPool:
+    """4 rotating batches in pinned host memory, handed out as zero-copy slices (what our arm's dataset does)."""
+
+    def __init__(self, shape, batch, steps, seed, torch, resident_device=None):
+        g = torch.Generator().manual_seed(seed)
+        self.x = torch.randn((4 * batch, *shape), generator=g)
+        self.y = torch.randint(0, 2, (4 * batch,), generator=g)
+        if resident_device is not None:
+            self.x, self.y = self.x.to(resident_device), self.y.to(resident_device)
+        else:
+            self.x, self.y = self.x.pin_memory(), self.y.pin_memory()
+        self.batch, self.steps = batch, steps
+
+    def __len__(self):
+        return self.steps
+
+    def __iter__(self):
+        b = self.batch
+        for i in range(self.steps):
+            j = (i % 4) * b
+            yield {'inputs': self.x[j:j + b], 'labels': self.y[j:j + b]}
+
+
+def run_r1(a):
+    import torch
+    import torch.distributed as dist
+    rank, local, aff = dist_setup(a.gpus)
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    from r1_nccl_cudnn import R1Step, launch_list
+    from coinstac_dinunet_b200.data.data import DevicePrefetcher
+    from coinstac_dinunet_b200.parallel.nvlink_learner import _LaggedReadback
+    torch.backends.cudnn.benchmark = True
+    dev = torch.device('cuda', local)
+    shape = VBM_SHAPE if a.model == 'vbm' else FS_SHAPE
+    batch = a.batch or (8 if a.model == 'vbm' else 16)
+    step = R1Step(a.model, shape, batch, dev, lr=1e-3, layout=a.layout, graph=bool(a.graph))
+    sampler = ClockSampler(local)
+
+    def run(k, resident, readback):
+        pool = _HostPool(shape, batch, k, 100 + rank, torch, resident_device=dev if resident else None)
+        it = pool if resident else DevicePrefetcher(pool, dev, depth=3)
+        rb = _LaggedReadback(dev) if readback else None
+
+        def go():
+            for b in it:
+                loss = step.step(b['inputs'], b['labels'])
+                if rb is not None:
+                    rb.push(loss)
+            if rb is not None:
+                rb.finish()
+        return go
+
+    run(a.warmup, True, False)()
+    go = run(a.steps, True, False)
+    sampler.start()
+    ms, _ = timed(go, dist, torch)
+    clocks = [sampler.stop()]
+    e2e = None
+    if not a.skip_e2e:
+        run(max(a.warmup, 3), False, True)()
+        go = run(a.steps, False, True)
+        sampler.start()
+        ms_e, _ = timed(go, dist, torch)
+        clocks.append(sampler.stop())
+        h2d = batch * (int(torch.tensor(shape).prod()) * 4 + 8)
+        e2e = {'value': a.gpus * batch * a.steps / (ms_e / 1e3), 'unit': 'samples/s', 'ms_per_step': ms_e / a.steps,
+               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'host_input_dtype': 'fp32'}
+    top = None
+    if rank == 0 and os.environ.get('COINN_R1_LAUNCHES'):
+        top = [[k, c, round(t, 1)] for k, c, t in launch_list(step)[:25]]
+    if rank == 0:
+        value = a.gpus * batch * a.steps / (ms / 1e3)
+        line = {'metric': metric_name(a.model), 'value': value, 'unit': 'samples/s', 'n_gpus': a.gpus, 'steps': a.steps,
+                'warmup': a.warmup, 'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic', 'impl': 'nccl_cudnn',
+                'config': {'model': 'RefVBMNet' if a.model == 'vbm' else 'RefFSNet', 'input': list(shape),
+                           'per_site_batch': batch, 'global_batch': batch * a.gpus,
+                           'parallelism': f'data parallel sites={a.gpus}: flat-grad NCCL all_reduce(AVG) + Adam(fused, capturable)',
+                           'memory_format': step.layout, 'autocast': 'bf16', 'cudnn_benchmark': True,
+                           'cuda_graph': bool(a.graph), 'affinity': aff},
+                'clocks': merge_clocks(*clocks), 'e2e': e2e, 'gpu_launches': 0}
+        if top:
+            line['top_kernels_us'] = top
         emit(line)
     dist.barrier(device_ids=[local])
     dist.destroy_process_group()
@@ -282,7 +466,7 @@ def run_reference(a):
         return
     import torch
     import torch.distributed as dist
-    rank, local = dist_setup(a.gpus)
+    rank, local, _aff = dist_setup(a.gpus)
     shape = VBM_SHAPE if a.model == 'vbm' else FS_SHAPE
     batch = a.batch or (8 if a.model == 'vbm' else 16)
     work = tempfile.mkdtemp(prefix='coinn_ref_') if rank == 0 else None
@@ -306,8 +490,7 @@ def run_reference(a):
         h2d = batch * (int(torch.tensor(shape).prod()) * 4 + 8)
         nparam = sum(p.numel() for p in eng.cache['nn']['model'].parameters())
         emit({
-            'metric': 'samples/sec (whole box, max over sites) VBM-3D-CNN dSGD' if a.model == 'vbm'
-            else 'samples/sec (whole box, max over sites) FreeSurfer-MLP dSGD',
+            'metric': metric_name(a.model),
             'value': value, 'unit': 'samples/s', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'fp32', 'data': 'synthetic', 'impl': 'reference',
@@ -329,5 +512,7 @@ if __name__ == '__main__':
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.impl == 'nccl_cudnn':
+        run_r1(args)
     else:
         run_ours(args)

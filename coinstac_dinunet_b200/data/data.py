@@ -78,53 +78,69 @@ def _seed_worker(worker_id):
 
 
 class DevicePrefetcher:
-    """Iterate a loader while staging the *next* batch on ``device`` via a copy stream.
+    """Iterate a loader while staging the next ``depth`` batches on ``device`` via a copy stream.
 
-    Batches must be (nested) dict/list/tuple of tensors; tensors are copied with
-    ``non_blocking=True`` from pinned memory, and the consumer stream waits on the copy
-    stream only when it takes the batch.
+    Batches must be (nested) dict/list/tuple of tensors; tensors are copied with ``non_blocking=True``
+    (a true async DMA when the host side is pinned).  Each staged batch carries an event: the consumer
+    stream waits on *that* copy only, so later copies keep running under the consumer's kernels.  On
+    hand-over every tensor is ``record_stream``-ed on the consumer stream - the caching allocator may
+    not recycle the block for a later copy while compute kernels still read it.
     """
 
-    def __init__(self, loader, device):
+    def __init__(self, loader, device, depth=2, stream=None):
         self.loader, self.device = loader, _torch.device(device)
+        self.depth = max(int(depth), 1)
         self.dataset = getattr(loader, 'dataset', None)
-        self._stream = _torch.cuda.Stream(self.device) if self.device.type == 'cuda' else None
+        self._stream = stream
+        if self._stream is None and self.device.type == 'cuda':
+            self._stream = _torch.cuda.Stream(self.device)
 
     def __len__(self):
         return len(self.loader)
 
-    def _to_dev(self, obj):
+    def _walk(self, obj, fn):
         if isinstance(obj, _torch.Tensor):
-            return obj.to(self.device, non_blocking=True)
+            return fn(obj)
         if isinstance(obj, dict):
-            return {k: self._to_dev(v) for k, v in obj.items()}
+            return {k: self._walk(v, fn) for k, v in obj.items()}
         if isinstance(obj, (list, tuple)):
-            return type(obj)(self._to_dev(v) for v in obj)
+            return type(obj)(self._walk(v, fn) for v in obj)
         return obj
+
+    def _to_dev(self, obj):
+        return self._walk(obj, lambda t: t.to(self.device, non_blocking=True))
 
     def __iter__(self):
         it = iter(self.loader)
         if self._stream is None:
             yield from it
             return
-        nxt = None
+        from collections import deque
+        staged = deque()
 
         def stage():
-            nonlocal nxt
             try:
                 host = next(it)
             except StopIteration:
-                nxt = None
-                return
+                return False
             with _torch.cuda.stream(self._stream):
-                nxt = self._to_dev(host)
+                dev = self._to_dev(host)
+                ev = _torch.cuda.Event()
+                ev.record(self._stream)
+            staged.append((dev, ev, host))           # `host` stays referenced until its DMA has been consumed
+            return True
 
-        stage()
-        while nxt is not None:
-            _torch.cuda.current_stream(self.device).wait_stream(self._stream)
-            cur = nxt
-            stage()
-            yield cur
+        more = True
+        while more and len(staged) < self.depth:
+            more = stage()
+        while staged:
+            dev, ev, _host = staged.popleft()
+            cur = _torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            self._walk(dev, lambda t: (t.record_stream(cur), t)[1] if t.is_cuda else t)
+            if more:
+                more = stage()
+            yield dev
 
 
 class COINNDataHandle:
@@ -204,8 +220,18 @@ class COINNDataHandle:
 
         loader = _DataLoader(collate_fn=merged.get('collate_fn', safe_collate), **largs)
         dev = merged.get('prefetch_to_device')
+        if dev is True:                                   # "the device this site trains on"
+            dev = (self.cache.get('device') or {}).get('gpu')
+            dev = dev if (dev is not None and _torch.device(dev).type == 'cuda') else None
         if dev:
-            return DevicePrefetcher(loader, dev)
+            dev = _torch.device(dev)
+            stream = None
+            if dev.type == 'cuda':                        # one copy stream per site, kept across rounds
+                streams = self.cache.setdefault('_prefetch_streams', {})
+                stream = streams.get(str(dev))
+                if stream is None:
+                    stream = streams[str(dev)] = _torch.cuda.Stream(dev)
+            return DevicePrefetcher(loader, dev, depth=int(merged.get('prefetch_depth', 2) or 2), stream=stream)
         return loader
 
     def next_iter(self, handle_key=Mode.TRAIN, shuffle=True) -> tuple:

@@ -18,6 +18,9 @@ import torch.distributed as _dist
 from .emulator import _clear_files, _copy_tree_flat, node_state, unwrap_spec
 
 
+AFFINITY = {}      # report of utils.affinity.pin_to_gpu for this process (empty on CPU)
+
+
 def init_process_group(backend=None):
     """Idempotent ``init_process_group`` from the torchrun environment (``127.0.0.1`` default)."""
     if _dist.is_initialized():
@@ -33,6 +36,9 @@ def init_process_group(backend=None):
         local = int(_os.environ.get('LOCAL_RANK', '0'))
         _torch.cuda.set_device(local)
         kw['device_id'] = _torch.device('cuda', local)
+        from ..utils.affinity import pin_to_gpu           # before any pinned allocation: NUMA-local staging buffers
+        world_local = int(_os.environ.get('LOCAL_WORLD_SIZE', _os.environ.get('WORLD_SIZE', '1')))
+        AFFINITY.update(pin_to_gpu(local, ranks_per_node=max(1, (world_local + 1) // 2)))
     _dist.init_process_group(backend=backend, **kw)
 
 

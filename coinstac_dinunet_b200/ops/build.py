@@ -18,8 +18,16 @@ OBJ_DIR = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, '_b200_ops.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
-FLAGS = ['-O3', '-std=c++17', '-lineinfo', '--use_fast_math', '-Xcompiler', '-fPIC',
-         '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
+BASE_FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
+              '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
+FLAGS = BASE_FLAGS + ['--use_fast_math']
+# Optimizer arithmetic is IEEE (sqrt / divide of the Adam update match torch.optim bit for bit up to summation order);
+# fast-math stays on for the conv / GEMM / normalisation kernels whose epilogues tolerate approximate rsqrt / exp.
+EXACT_MATH = {'fused_reduce_opt.cu', 'powersgd.cu', 'rankdad.cu'}
+
+
+def flags_for(src):
+    return BASE_FLAGS if os.path.basename(src) in EXACT_MATH else FLAGS
 
 
 def sources():
@@ -31,7 +39,7 @@ def _digest(path):
     for p in [path] + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))):
         with open(p, 'rb') as fp:
             h.update(fp.read())
-    h.update(' '.join(ARCH + FLAGS).encode())
+    h.update(' '.join(ARCH + flags_for(path)).encode())
     return h.hexdigest()
 
 
@@ -41,7 +49,7 @@ def _compile(src, verbose):
     dig = _digest(src)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, False
-    cmd = [NVCC, *ARCH, *FLAGS, '-I', CSRC, '-c', src, '-o', obj]
+    cmd = [NVCC, *ARCH, *flags_for(src), '-I', CSRC, '-c', src, '-o', obj]
     if verbose:
         print(' '.join(cmd), flush=True)
     subprocess.run(cmd, check=True)

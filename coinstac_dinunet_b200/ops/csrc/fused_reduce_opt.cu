@@ -43,15 +43,21 @@ struct FusedArgs {
     int*        step;                   // local device step counter (Adam bias correction)
     uint32_t*   ticket;                 // local, last-CTA detection
     const float* lr_ptr;                // optional device-side learning rate (graph-safe schedules)
+    float*      grad32;                 // grad_dtype != F32: the local fp32 gradient arena autograd accumulates into; it is
+                                        // packed into this rank's 16-bit wire buffer (= grad_ptrs[rank]) before the start barrier
+    int*        error;                  // local watchdog word: 0 = healthy, 1 + peer = that peer never arrived at a barrier
     long long   offset;                 // first element of the bucket (multiple of 4)
     long long   numel;                  // elements in the bucket (multiple of 4)
     float lr, beta1, beta2, eps, weight_decay, grad_scale, momentum;
     int rank, world, variant, opt_kind, grad_dtype, zero_grads, bump_step, nesterov;
+    unsigned timeout_ms;                // bounded spin of the cross-GPU barrier (0 = spin forever)
+    int _pad;
 };
 
 // ------------------------------------------------------------------------------------------------
 template <int GD> struct GradIO;
 template <> struct GradIO<G_F32> {
+    static __device__ __forceinline__ void store(void*, long long, const float4&) {}
     static __device__ __forceinline__ float4 load(const void* base, long long vec) {
         return ld_stream_f4(reinterpret_cast<const float4*>(base) + vec);
     }
@@ -63,6 +69,9 @@ template <> struct GradIO<G_F32> {
     }
 };
 template <> struct GradIO<G_BF16> {
+    static __device__ __forceinline__ void store(void* base, long long vec, const float4& g) {
+        reinterpret_cast<uint2*>(base)[vec] = make_uint2(pack_bf16x2(g.x, g.y), pack_bf16x2(g.z, g.w));
+    }
     static __device__ __forceinline__ float4 load(const void* base, long long vec) {
         uint2 u = ld_stream_u2(reinterpret_cast<const uint2*>(base) + vec);
         float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
@@ -81,6 +90,10 @@ template <> struct GradIO<G_BF16> {
     }
 };
 template <> struct GradIO<G_F16> {
+    static __device__ __forceinline__ void store(void* base, long long vec, const float4& g) {
+        __half2 a = __floats2half2_rn(g.x, g.y), b = __floats2half2_rn(g.z, g.w);
+        reinterpret_cast<uint2*>(base)[vec] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
     static __device__ __forceinline__ float4 load(const void* base, long long vec) {
         uint2 u = ld_stream_u2(reinterpret_cast<const uint2*>(base) + vec);
         float2 a = unpack_f16x2(u.x), b = unpack_f16x2(u.y);
@@ -98,15 +111,40 @@ template <> struct GradIO<G_F16> {
     }
 };
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // Cross-GPU barrier between the CTAs with the same blockIdx on every rank.  Flags only ever
 // grow (sequence numbers), so there is no reset race; one writer per slot.
+// Watchdog: the spin is bounded by `timeout_ms` of wall time (%globaltimer, polled every 1024 probes).  A CTA that
+// gives up records `1 + peer` in the local error word; once the word is set every later barrier of this rank falls
+// straight through, so a dead site costs one timeout, not a hung box - the host raises after the round
+// (DistArena.check_health).  The numerical result of such a step is garbage by construction.
 __device__ __forceinline__ void cta_barrier_all_ranks(const FusedArgs& a, int block, uint32_t seq) {
     __syncthreads();
     if (threadIdx.x < a.world) {
         const int peer = threadIdx.x;
         st_release_sys(a.flag_ptrs[peer] + block * kMaxRanks + a.rank, seq);
         const uint32_t* mine = a.flag_ptrs[a.rank] + block * kMaxRanks + peer;
-        while ((int32_t)(ld_acquire_sys(mine) - seq) < 0) { }
+        volatile int* err = a.error;
+        if (!(err && *err)) {
+            unsigned probes = 0;
+            unsigned long long t0 = 0;
+            while ((int32_t)(ld_acquire_sys(mine) - seq) < 0) {
+                if (a.timeout_ms && ((++probes & 1023u) == 0u)) {
+                    const unsigned long long now = global_ns();
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > (unsigned long long)a.timeout_ms * 1000000ull) {
+                        if (err) atomicCAS(a.error, 0, 1 + peer);
+                        break;
+                    }
+                    if (err && *err) break;
+                }
+            }
+        }
     }
     __syncthreads();
 }
@@ -158,8 +196,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_reduce_opt_kernel(const Fus
         h.bc2_rsqrt = (float)(1.0 / sqrt(bc2));
     } else { h.bc1_inv = 1.f; h.bc2_rsqrt = 1.f; }
 
-    if (multi) cta_barrier_all_ranks(a, b, 2u * seq - 1u);
-
     // ---- which vectors (4 elements each) does this CTA own? ----
     const long long nvec = a.numel >> 2, off = a.offset >> 2;
     long long shard = nvec, s_lo = 0, s_hi = nvec;
@@ -170,6 +206,29 @@ __global__ void __launch_bounds__(kThreads, 1) fused_reduce_opt_kernel(const Fus
     }
     const long long chunk = (shard + G - 1) / G;     // identical on every rank
     const long long lo = min(s_lo + (long long)b * chunk, s_hi), hi = min(lo + chunk, s_hi);
+
+    // ---- 16-bit wire (precision_bits = 16): pack my fp32 gradients into my wire buffer - exactly the slices that the
+    //      CTAs with MY block index read on the peers, so the per-block barrier below orders pack -> peer loads ----
+    if (GD != G_F32 && multi) {
+        float4* g32 = reinterpret_cast<float4*>(a.grad32) + off;
+        void* wire = const_cast<void*>(a.grad_ptrs[r]);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int nq = (VAR == ONE_SHOT) ? 1 : S;
+        for (int q = 0; q < nq; ++q) {
+            long long z_lo = lo, z_hi = hi;
+            if (VAR != ONE_SHOT) {
+                const long long q_lo = min((long long)q * shard, nvec), q_hi = min(q_lo + shard, nvec);
+                z_lo = min(q_lo + (long long)b * chunk, q_hi); z_hi = min(z_lo + chunk, q_hi);
+            }
+            for (long long i = z_lo + tid; i < z_hi; i += kThreads) {
+                GradIO<GD>::store(wire, off + i, g32[i]);
+                if (a.zero_grads) g32[i] = z4;         // the fp32 arena is private: re-zero it right here
+            }
+        }
+        __threadfence_system();
+    }
+
+    if (multi) cta_barrier_all_ranks(a, b, 2u * seq - 1u);
 
     float4* __restrict__ P = reinterpret_cast<float4*>(a.param_ptrs[r]) + off;
     float4* __restrict__ M = reinterpret_cast<float4*>(a.m) + off;
@@ -229,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_reduce_opt_kernel(const Fus
     }
 
     // ---- my gradient slices have been consumed by every peer: clear them for the next step ----
-    if (a.zero_grads) {
+    if (a.zero_grads && (GD == G_F32 || !multi)) {   // (16-bit wire: the fp32 arena was re-zeroed while packing)
         void* mine = const_cast<void*>(a.grad_ptrs[r]);
         if (!multi || VAR == ONE_SHOT) {
             for (long long i = lo + tid; i < hi; i += kThreads) GradIO<GD>::zero(mine, off + i);
@@ -283,6 +342,8 @@ COINN_API int coinn_fused_reduce_opt(const coinn::FusedArgs* args, int grid, voi
     FusedArgs a = *args;
     if (a.world < 1 || a.world > kMaxRanks || (a.numel & 3) || (a.offset & 3)) return (int)cudaErrorInvalidValue;
     if (a.numel == 0) return 0;
+    if (a.world == 1) a.grad_dtype = G_F32;                       // no wire without peers
+    if (a.grad_dtype != G_F32 && a.grad32 == nullptr) return (int)cudaErrorInvalidValue;
     const long long nvec = a.numel >> 2;
     long long per_rank = (a.world > 1 && a.variant != ONE_SHOT) ? (nvec + a.world - 1) / a.world : nvec;
     if (grid <= 0) {

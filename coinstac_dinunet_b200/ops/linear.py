@@ -92,7 +92,29 @@ class LinearFn(_torch.autograd.Function):
         return dx, dw, db, None
 
 
-DIRECT_GRAD_DISABLED = False      # set by DistArena.enable_overlap(): bucket launches are driven by post-accumulate-grad hooks
+DIRECT_GRAD_DISABLED = False      # debugging switch: force every gradient through autograd's AccumulateGrad
+
+# Kernels that accumulate straight into ``param.grad`` hand ``None`` to autograd, so ``post_accumulate_grad`` hooks never
+# fire for those parameters.  Whoever needs to know "this gradient is final" (DistArena's bucketed backward overlap)
+# registers a listener here and the direct-mode kernels call ``notify_grad_written`` right after their launch.
+import weakref as _weakref
+
+_GRAD_LISTENERS = _weakref.WeakKeyDictionary()
+
+
+def register_grad_listener(param, fn):
+    _GRAD_LISTENERS[param] = fn
+
+
+def notify_grad_written(*params):
+    if not _GRAD_LISTENERS:
+        return
+    for q in params:
+        if q is None:
+            continue
+        fn = _GRAD_LISTENERS.get(q)
+        if fn is not None:
+            fn()
 
 
 def direct_grad_ok(param):
@@ -155,6 +177,7 @@ class SmallLinearFn(_torch.autograd.Function):
         if dx is not None and x.dtype != _torch.float32:
             dx = dx.to(x.dtype)
         if direct:
+            notify_grad_written(weight, bias if need_b else None)
             return dx, None, None, None
         return dx, dw.to(weight.dtype), (db.to(bias.dtype) if db is not None else None), None
 

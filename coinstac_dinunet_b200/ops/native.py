@@ -17,12 +17,13 @@ class FusedArgs(C.Structure):
         ('shadow_ptrs', C.c_void_p * MAX_RANKS), ('flag_ptrs', C.c_void_p * MAX_RANKS),
         ('grad_mc', C.c_void_p), ('param_mc', C.c_void_p), ('shadow_mc', C.c_void_p),
         ('m', C.c_void_p), ('v', C.c_void_p), ('epoch', C.c_void_p), ('step', C.c_void_p),
-        ('ticket', C.c_void_p), ('lr_ptr', C.c_void_p),
+        ('ticket', C.c_void_p), ('lr_ptr', C.c_void_p), ('grad32', C.c_void_p), ('error', C.c_void_p),
         ('offset', C.c_longlong), ('numel', C.c_longlong),
         ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
         ('weight_decay', C.c_float), ('grad_scale', C.c_float), ('momentum', C.c_float),
         ('rank', C.c_int), ('world', C.c_int), ('variant', C.c_int), ('opt_kind', C.c_int),
         ('grad_dtype', C.c_int), ('zero_grads', C.c_int), ('bump_step', C.c_int), ('nesterov', C.c_int),
+        ('timeout_ms', C.c_uint), ('_pad', C.c_int),
     ]
 
 

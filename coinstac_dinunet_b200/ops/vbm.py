@@ -109,6 +109,8 @@ def conv_block_grad_finalize(dwt, acc, conv_w, gamma, beta, cin, cout, transpose
                                                    beta.grad.data_ptr(), cin, cout, int(transposed), _sp(dwt)),
          'coinn_conv_block_grad_finalize')
     _bump()
+    from .linear import notify_grad_written
+    notify_grad_written(conv_w, gamma, beta)         # direct mode: autograd never sees these gradients
 
 
 def conv1_fused_enabled():

@@ -116,6 +116,7 @@ class GraphedStep:
         from .. import ops as _ops
         for k, v in _flatten_batch(batch).items():
             self.static[k].copy_(v, non_blocking=True)
+        self.arena.sync_lr()            # the graph reads the learning rate from a device scalar: schedulers keep working
         self.graph.replay()
         self.arena.steps_done += 1
         self.arena.host_step += 1

@@ -16,12 +16,14 @@ by round.
 The same code runs on CPU with the gloo backend (``DistArena`` falls back to all-reduce +
 ``optimizer.step``), which is how the host-side logic is tested without a GPU.
 """
+import time as _time
+
 import torch as _torch
 import torch.distributed as _dist
 
 from ..config.keys import Mode, Transport
 from ..distrib.learner import COINNLearner
-from .arena import DistArena
+from .arena import DistArena, wire_dtype_for
 
 
 def _dist_on():
@@ -30,39 +32,79 @@ def _dist_on():
 
 class _LaggedReadback:
     """Per-step device->host read of the loss without stalling the launch pipeline: step t's loss is copied
-    asynchronously into a pinned slot and *consumed* (event-synchronised) while step t+1 is already queued."""
+    asynchronously into a slot of a pinned ring and *consumed* (event-synchronised) ``lag`` steps later, so the host
+    runs up to ``lag`` steps ahead of the device and a scheduling hiccup of a few milliseconds never drains the GPU
+    queue.  The ring is allocated once per site (``cache['_readback']``) - pinning host memory inside the round costs
+    a driver call that serialises against every other rank of the box."""
 
-    def __init__(self, device, slots=4):
-        self.buf = _torch.zeros(slots, dtype=_torch.float32).pin_memory() if device.type == 'cuda' else _torch.zeros(slots)
-        self.events = [None] * slots
-        self.slots, self.count, self.head, self.last = slots, 0, 0, float('nan')
+    def __init__(self, device, slots=8, lag=4):
         self.cuda = device.type == 'cuda'
+        self.buf = _torch.zeros(slots, dtype=_torch.float32)
+        if self.cuda:
+            self.buf = self.buf.pin_memory()
+        self.events = [_torch.cuda.Event() for _ in range(slots)] if self.cuda else [None] * slots
+        self.slots, self.lag = slots, min(lag, slots - 1)
+        self.reset()
+
+    def reset(self):
+        self.pending = [False] * self.slots
+        self.count, self.head, self.last = 0, 0, float('nan')
+        return self
+
+    @classmethod
+    def for_site(cls, cache, device):
+        rb = cache.get('_readback')
+        if rb is None or rb.cuda != (device.type == 'cuda'):
+            rb = cache['_readback'] = cls(device, slots=int(cache.get('readback_slots', 8)),
+                                          lag=int(cache.get('readback_lag', 4)))
+        return rb.reset()
 
     def _consume(self, i):
-        if self.events[i] is not None:
-            self.events[i].synchronize()
+        if self.pending[i]:
+            if self.cuda:
+                self.events[i].synchronize()
             self.last = float(self.buf[i])
-            self.events[i] = None
+            self.pending[i] = False
             self.count += 1
 
     def push(self, loss):
         i = self.head % self.slots
-        self._consume(i)                                   # slot reuse => at most `slots-1` steps of lag
+        self._consume(i)                                   # slot reuse bounds the lag even if `lag` >= slots
         self.buf[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
         if self.cuda:
-            ev = _torch.cuda.Event()
-            ev.record()
-            self.events[i] = ev
-        else:
-            self.last, self.count = float(self.buf[i]), self.count + 1
-        if self.head >= 1:
-            self._consume((self.head - 1) % self.slots)    # read step t-1 now that step t is queued
+            self.events[i].record()
+        self.pending[i] = True
+        if self.head >= self.lag:
+            self._consume((self.head - self.lag) % self.slots)   # read step t-lag now that step t is queued
         self.head += 1
 
     def finish(self):
-        for i in range(self.slots):
-            self._consume((self.head + i) % self.slots)
+        for k in range(self.slots):
+            self._consume((self.head + k) % self.slots)
         return self.last
+
+
+class _RunningScores:
+    """Folds every step's ``averages`` / ``metrics`` into two accumulators so an epoch of fused steps keeps O(1)
+    iteration dicts alive instead of O(steps) (loss / logits / prediction tensors of every step)."""
+
+    def __init__(self, trainer):
+        self.trainer = trainer
+        self.avg, self.met, self.last = trainer.new_averages(), trainer.new_metrics(), None
+
+    def add(self, its):
+        for it in its:
+            if it.get('averages') is not None:
+                self.avg.accumulate(it['averages'])
+            if it.get('metrics') is not None:
+                self.met.accumulate(it['metrics'])
+        if its:
+            self.last = its[-1]
+
+    def result(self):
+        out = dict(self.trainer.reduce_iteration([self.last])) if self.last is not None else {}
+        out['averages'], out['metrics'] = self.avg, self.met
+        return out
 
 
 class NvlinkLearner(COINNLearner):
@@ -79,7 +121,10 @@ class NvlinkLearner(COINNLearner):
                 backend = 'torch'
             arena = DistArena(self.model, self.optim, device=self.device, backend=backend,
                               variant=self.cache.get('reduce_variant', 'auto'),
-                              shadow_bf16=bool(self.cache.get('shadow_bf16', False)))
+                              shadow_bf16=bool(self.cache.get('shadow_bf16', False)),
+                              grad_dtype=wire_dtype_for(self.cache),
+                              timeout_ms=(float(self.cache['barrier_timeout_s']) * 1e3
+                                          if self.cache.get('barrier_timeout_s') else None))
             if self.cache.get('overlap_backward') and self._overlap_ok:
                 arena.enable_overlap(int(self.cache.get('bucket_bytes', 4 << 20)))
             self.cache['_arena'] = arena
@@ -129,14 +174,17 @@ class NvlinkLearner(COINNLearner):
             gs = self.cache['_graph_step'] = GraphedStep(self).capture(batch)   # state is rolled back after warm-up
             gs.step(batch)                                                       # ... so this is training step 1
             done = 1
-        rb = _LaggedReadback(self.device) if self.cache.get('readback_per_step') else None
+        rb = _LaggedReadback.for_site(self.cache, self.device) if self.cache.get('readback_per_step') else None
         if rb is not None and done:
             rb.push(gs.it['loss'])
+        stamps = self.cache.get('_host_stamps')             # bench/diagnostics: host time at which each step was queued
         for _ in range(steps - done):
             batch, _ = self.trainer.data_handle.next_iter()
             gs.step(batch)
             if rb is not None:
                 rb.push(gs.it['loss'])
+            if stamps is not None:
+                stamps.append(_time.perf_counter())
         if rb is not None:
             self.cache['last_loss'] = rb.finish()
             self.cache['losses_read'] = rb.count
@@ -149,15 +197,17 @@ class NvlinkLearner(COINNLearner):
                      and self.cache.get('local_iterations', 1) == 1 and self.arena.backend == 'nvlink')
         if graphable:
             it = self._graphed_round(self._steps_this_round())
+            self.arena.check_health()                     # barrier watchdog: a site that never arrived raises here
             self.cache['cursor'] = 0
             out['mode'] = Mode.VALIDATION_WAITING
             out['fused_steps'] = self.arena.steps_done
             return it, out
-        rb = _LaggedReadback(self.device) if self.cache.get('readback_per_step') else None
+        rb = _LaggedReadback.for_site(self.cache, self.device) if self.cache.get('readback_per_step') else None
         timer = None
         if self.cache.get('profile'):                     # compspec-style "profile": true -> per-phase device timers
             from ..utils.profiling import DeviceTimer
             timer = self.cache.setdefault('_profile_timer', DeviceTimer(self.device if self.device.type == 'cuda' else None))
+        scores = _RunningScores(self.trainer)
         for _ in range(self._steps_this_round()):
             if timer is not None:
                 with timer('forward_backward'):
@@ -169,18 +219,19 @@ class NvlinkLearner(COINNLearner):
                 self.arena.reduce_and_step()
             if rb is not None:                            # end-to-end mode: every step's loss goes to the host
                 rb.push(step_its[-1]['loss'])
-            its.extend(step_its)
+            scores.add(step_its)
         if rb is not None:
             self.cache['last_loss'] = rb.finish()
             self.cache['losses_read'] = rb.count
         if timer is not None:
             from ..utils.profiling import site_profile
             out['profile'] = site_profile(self.cache, timer, key='profile_log')
+        self.arena.check_health()
         # the round IS the epoch: report it finished regardless of where the local cursor is
         self.cache['cursor'] = 0
         out['mode'] = Mode.VALIDATION_WAITING
         out['fused_steps'] = self.arena.steps_done
-        return self.trainer.reduce_iteration(its), out
+        return scores.result(), out
 
 
 class NvlinkPowerSGDLearner(NvlinkLearner):
@@ -248,18 +299,22 @@ class NvlinkPowerSGDLearner(NvlinkLearner):
         self.arena.local_step()
 
     def to_reduce(self):
-        its, out = [], {}
+        out, scores = {}, _RunningScores(self.trainer)
         for _ in range(self._steps_this_round()):
             step_its, _ = self.backward()
             if self.st.iter < self.start_iter:
                 self.arena.reduce_and_step()
             else:
+                if self.st.iter == self.start_iter:
+                    # warm-up ran sharded updates (two-shot / NVLS: rank r holds the Adam moments of shard r only);
+                    # the compressed phase updates the full range locally, so every site needs the complete moments
+                    self.arena.gather_state()
                 self._compressed_step()
             self.st.iter += 1
-            its.extend(step_its)
+            scores.add(step_its)
         self.cache['cursor'] = 0
         out['mode'] = Mode.VALIDATION_WAITING
-        return self.trainer.reduce_iteration(its), out
+        return scores.result(), out
 
 
 class NvlinkDADLearner(NvlinkLearner):
@@ -314,16 +369,16 @@ class NvlinkDADLearner(NvlinkLearner):
         self.arena.local_step()
 
     def to_reduce(self):
-        its, out = [], {}
+        out, scores = {}, _RunningScores(self.trainer)
         saved = self.cache.get('local_iterations', 1)
         self.cache['local_iterations'] = 1          # rankDAD cannot accumulate gradients
         try:
             for _ in range(self._steps_this_round()):
                 step_its, _ = self.backward()
                 self._dad_step()
-                its.extend(step_its)
+                scores.add(step_its)
         finally:
             self.cache['local_iterations'] = saved
         self.cache['cursor'] = 0
         out['mode'] = Mode.VALIDATION_WAITING
-        return self.trainer.reduce_iteration(its), out
+        return scores.result(), out

@@ -89,6 +89,8 @@ def save_cache(cache, log_dir):
     """
     snapshot = {}
     for k in cache.keys():
+        if str(k).startswith('_') and str(k) != '_args_cached_':
+            continue          # private runtime objects (device arenas, CUDA graphs, streams): never worth a deep copy
         try:
             snapshot[str(k)] = _copy.deepcopy(cache[k])
         except Exception:

@@ -92,7 +92,7 @@ def scenario_overlap(work, opts):
         m2.load_state_dict(m1.state_dict())
         a1 = DistArena(m1, torch.optim.Adam(m1.parameters(), lr=1e-2), device=dev, backend='nvlink', variant=variant)
         a2 = DistArena(m2, torch.optim.Adam(m2.parameters(), lr=1e-2), device=dev, backend='nvlink', variant=variant)
-        a2.enable_overlap(bucket_bytes=128 << 10)
+        a2.enable_overlap(bucket_bytes=64 << 10)
         for step in range(6):
             g = torch.Generator(device='cpu').manual_seed(77 * step + rank)
             x = torch.randn(16, 257, generator=g).to(dev)
@@ -105,15 +105,155 @@ def scenario_overlap(work, opts):
             how = a2.reduce_and_step()
         torch.cuda.synchronize()
         err = float((a1.flat_param - a2.flat_param).abs().max())
+        # checkpoint path: sharded moments gathered per launch unit must agree between the two launch schedules
+        a1.gather_state(); a2.gather_state()
+        torch.cuda.synchronize()
+        state_err = max(float((a1.m - a2.m).abs().max()), float((a1.v - a2.v).abs().max()))
         mine = a2.flat_param.clone()
         allp = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allp, mine)
-        results.append({'variant': variant, 'how': how, 'err': err, 'buckets': len(a2._overlap['buckets']),
+        results.append({'variant': variant, 'how': how, 'err': err, 'state_err': state_err, 'buckets': len(a2._overlap['buckets']),
                         'identical': all(torch.equal(allp[0], q) for q in allp[1:]),
                         'steps': int(a2.step_count), 'zeroed': float(a2.flat_grad.abs().max()) == 0.0})
     if rank == 0:
         with open(os.path.join(work, 'result.json'), 'w') as fp:
             json.dump({'results': results, 'world': world}, fp)
 
+class _Flat(torch.nn.Module):
+    """One flat parameter of `n` elements: the fused kernel sees exactly the requested size."""
 
-SCENARIOS = {'fused': scenario_fused, 'allreduce': scenario_allreduce, 'overlap': scenario_overlap}
+    def __init__(self, n, dev):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(n, device=dev))
+
+
+def _adam_ref(p, m, v, g, t, lr=1e-2, b1=0.9, b2=0.999, eps=1e-8):
+    m.mul_(b1).add_(g, alpha=1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    denom = (v.sqrt() / (1 - b2 ** t) ** 0.5).add_(eps)
+    p.addcdiv_(m, denom, value=-lr / (1 - b1 ** t))
+
+
+def scenario_sizes(work, opts):
+    """fused reduce + Adam on 1 KB, 1 MB + 4 B, 64 MB (and 1 GB with big=1) of gradients, every variant, two steps,
+    against a plain torch Adam on the exactly averaged gradient."""
+    from coinstac_dinunet_b200.parallel.arena import DistArena
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    sizes = [256, (1 << 18) + 1, 1 << 24] + ([1 << 28] if opts.get('big') == '1' else [])
+    results = []
+    for n in sizes:
+        for variant in ('one_shot', 'two_shot', 'nvls'):
+            if variant == 'one_shot' and n > (1 << 24):
+                continue
+            model = _Flat(n, dev)
+            with torch.no_grad():
+                model.w.copy_(torch.linspace(-1, 1, n, device=dev))
+            arena = DistArena(model, torch.optim.Adam(model.parameters(), lr=1e-2), device=dev, backend='nvlink', variant=variant)
+            p, m, v = model.w.detach().clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+            used = None
+            for t in (1, 2):
+                gen = torch.Generator(device=dev).manual_seed(1000 * t + rank)
+                g = torch.randn(n, device=dev, generator=gen) * (rank + 1)
+                model.w.grad.copy_(g)
+                mean = g.clone()
+                dist.all_reduce(mean)
+                mean /= world
+                _adam_ref(p, m, v, mean, t)
+                del g, mean
+                used = arena.reduce_and_step()
+            torch.cuda.synchronize()
+            err = float((model.w.detach() - p).abs().max())
+            zeroed = float(arena.flat_grad.abs().max()) == 0.0
+            mine = arena.flat_param[:n].clone()
+            ref0 = mine.clone()
+            dist.broadcast(ref0, src=0)
+            same = torch.tensor([float(torch.equal(ref0, mine))], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            arena.check_health()
+            results.append({'numel': n, 'variant': variant, 'used': used, 'err': err, 'zeroed': zeroed,
+                            'identical': bool(same.item())})
+            del arena, model, p, m, v, mine, ref0
+            torch.cuda.empty_cache()
+    if rank == 0:
+        with open(os.path.join(work, 'result.json'), 'w') as fp:
+            json.dump({'results': results, 'world': world}, fp)
+
+
+def scenario_wire16(work, opts):
+    """precision_bits = 16 on the NVLink transport: gradients cross the wire as fp16 / bf16 (packed inside the fused
+    kernel), are summed in fp32 and the optimizer runs on fp32 masters.  Oracle: Adam on the mean of the ROUNDED
+    per-site gradients (what the reference computes: learner.py:17 casts, reducer.py:29 means)."""
+    from coinstac_dinunet_b200.parallel.arena import DistArena
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    results = []
+    for wire, tdt in (('bf16', torch.bfloat16), ('f16', torch.float16)):
+        for variant in ('one_shot', 'two_shot', 'nvls'):
+            for n in (1000, (1 << 20) + 4):
+                model = _Flat(n, dev)
+                arena = DistArena(model, torch.optim.Adam(model.parameters(), lr=1e-2), device=dev, backend='nvlink',
+                                  variant=variant, grad_dtype=wire)
+                assert arena.wire_buf is not None and arena.grad_code in (1, 2)
+                p, m, v = model.w.detach().clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+                for t in (1, 2, 3):
+                    gen = torch.Generator(device=dev).manual_seed(77 * t + rank)
+                    g = torch.randn(n, device=dev, generator=gen)
+                    model.w.grad.copy_(g)
+                    mean = g.to(tdt).float()
+                    dist.all_reduce(mean)
+                    mean /= world
+                    _adam_ref(p, m, v, mean, t)
+                    used = arena.reduce_and_step()
+                torch.cuda.synchronize()
+                err = float((model.w.detach() - p).abs().max())
+                zeroed = float(arena.flat_grad.abs().max()) == 0.0
+                mine = arena.flat_param[:n].clone()
+                ref0 = mine.clone()
+                dist.broadcast(ref0, src=0)
+                same = torch.tensor([float(torch.equal(ref0, mine))], device=dev)
+                dist.all_reduce(same, op=dist.ReduceOp.MIN)
+                results.append({'wire': wire, 'variant': variant, 'used': used, 'numel': n, 'err': err, 'zeroed': zeroed,
+                                'identical': bool(same.item())})
+    if rank == 0:
+        with open(os.path.join(work, 'result.json'), 'w') as fp:
+            json.dump({'results': results, 'world': world}, fp)
+
+
+def scenario_watchdog(work, opts):
+    """A site that never arrives must not hang the box: rank `world-1` launches its step 3 s late, the others run with a
+    0.5 s barrier timeout.  Their kernels give up, record which peer was missing and `check_health` raises; the late
+    rank then finds everybody's flags already posted and terminates too."""
+    from coinstac_dinunet_b200.parallel.arena import DistArena
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    model = _Flat(4096, dev)
+    arena = DistArena(model, torch.optim.Adam(model.parameters(), lr=1e-2), device=dev, backend='nvlink',
+                      variant='one_shot', timeout_ms=500)
+    model.w.grad.fill_(1.0)
+    arena.reduce_and_step()                      # a healthy step first
+    torch.cuda.synchronize()
+    arena.check_health()
+    dist.barrier()
+    late = world - 1
+    t0 = time.time()
+    if rank == late:
+        time.sleep(3.0)
+    model.w.grad.fill_(1.0)
+    arena.reduce_and_step()
+    torch.cuda.synchronize()
+    waited = time.time() - t0
+    raised, msg = False, ''
+    try:
+        arena.check_health()
+    except RuntimeError as exc:
+        raised, msg = True, str(exc)
+    out = [None] * world
+    dist.all_gather_object(out, {'rank': rank, 'raised': raised, 'msg': msg, 'waited': waited})
+    if rank == 0:
+        with open(os.path.join(work, 'result.json'), 'w') as fp:
+            json.dump({'results': out, 'world': world, 'late': late}, fp)
+
+
+SCENARIOS = {'fused': scenario_fused, 'allreduce': scenario_allreduce, 'overlap': scenario_overlap,
+             'sizes': scenario_sizes, 'wire16': scenario_wire16, 'watchdog': scenario_watchdog}

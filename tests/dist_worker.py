@@ -21,7 +21,9 @@ def scenario_protocol(work, opts):
                 batch_size=4, num_folds=None, split_ratio=[0.6, 0.2, 0.2], learning_rate=1e-2, seed=7,
                 transport=opts.get('transport', 'nvlink'), agg_engine=opts.get('agg_engine', 'dSGD'),
                 start_powerSGD_iter=2, matrix_approximation_rank=2, cuda_graph=opts.get('cuda_graph') == '1',
-                epochs=int(opts.get('epochs', 2)),
+                epochs=int(opts.get('epochs', 2)), reduce_variant=opts.get('reduce_variant', 'auto'),
+                overlap_backward=opts.get('overlap') == '1', bucket_bytes=int(opts.get('bucket_bytes', 64 << 10)),
+                precision_bits=int(opts.get('precision_bits', 32)),
                 gpus=[int(os.environ.get('LOCAL_RANK', 0))] if torch.cuda.is_available() else None)
     eng = DistEngine(work, inputspec=spec)
     sizes = [24, 18, 30, 12, 20, 16, 28, 22]

@@ -400,7 +400,7 @@ def test_bucketed_backward_overlap_equals_single_launch(dev):
     (m1, o1), (m2, o2) = make(), make()
     a1 = DistArena(m1, o1, device=dev, backend='nvlink')
     a2 = DistArena(m2, o2, device=dev, backend='nvlink').enable_overlap(bucket_bytes=256 << 10)
-    assert len(a2._overlap['buckets']) >= 3
+    assert len(a2._overlap['buckets']) >= 2
     for step in range(5):
         x = torch.randn(32, 300, device=dev)
         m1(x).square().mean().backward(); a1.reduce_and_step()
