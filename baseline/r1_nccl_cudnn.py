@@ -43,8 +43,8 @@ class R1Step:
         params = [p for p in self.model.parameters()]
         self.flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=device)
         off = 0
-        for p in params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+        for p in params:          # same strides as the parameter (channels_last_3d weights are permuted-dense): fused Adam
+            p.grad = torch.as_strided(self.flat, p.shape, p.stride(), off)   # wants identical layouts
             off += p.numel()
         self.params = params
         self.opt = torch.optim.Adam(params, lr=lr, fused=True, capturable=True)

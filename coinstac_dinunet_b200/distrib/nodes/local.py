@@ -31,6 +31,17 @@ def _engine_learners():
     return {AGG_Engine.dSGD: _dSGDLearner, AGG_Engine.rankDAD: DADLearner, AGG_Engine.powerSGD: PowerSGDLearner}
 
 
+class _Round:
+    """What one engine round carries between handlers (the node object itself is rebuilt every round)."""
+    __slots__ = ('mp_pool', 'trainer_cls', 'dataset_cls', 'datahandle_cls', 'learner_cls', 'trainer', 'learner', 'modes')
+
+    def __init__(self, **kw):
+        self.trainer = self.learner = None
+        self.modes = []
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
 class COINNLocal:
     _PROMPT_TASK_ = "Task id must be given."
     _PROMPT_MODE_ = f"Mode must be provided and should be one of {[Mode.TRAIN.value, Mode.TEST.value]}."
@@ -147,75 +158,125 @@ class COINNLocal:
         return out
 
     # ------------------------------------------------------------------ compute
+    # The site is a table-driven machine.  One round = (1) the ENTRY handler of the phase the aggregator sent,
+    # (2) learner construction + mode echo, (3) the EXIT handler of the phase the entry handler left in ``out``.
+    # The computation phase is itself a rule table over (input flags, global modes): every rule whose guard holds
+    # fires, in order.  Adding a phase / a rule is a table entry, not another branch.
+    def _enter_init_runs(self, rt):
+        self.out.update(**self._init_runs(rt.trainer))
+        # share the constructor-level arguments with the aggregator and freeze them
+        shared = {k: self.cache[k] for k in self._args}
+        # also share what the aggregator needs to build the same metric objects
+        for k in ('num_class', *self.cache.get('shared_keys', ())):
+            if k in self.cache and k not in shared:
+                shared[k] = self.cache[k]
+        self.cache['frozen_args'] = _FrozenDict(shared)
+        self.out['shared_args'] = self.cache['frozen_args']
+
+    def _enter_next_run(self, rt):
+        self.cache.update(**self.input['global_runs'][self.state['clientId']])
+        self.out.update(**self._next_run(rt.trainer))
+        if self.cache['mode'] == Mode.TRAIN:
+            dh = rt.trainer.data_handle
+            self.out.update(**self._pretrain_local(rt.trainer_cls, rt.datahandle_cls,
+                                                   dh.get_train_dataset(rt.dataset_cls),
+                                                   dh.get_validation_dataset(rt.dataset_cls)))
+
+    def _enter_pre_computation(self, rt):
+        if not self.input.get('pretrained_weights'):
+            return
+        path = self.state['baseDirectory'] + _sep + self.input['pretrained_weights']
+        if not self._device_broadcast(rt, path):
+            rt.trainer.load_checkpoint(file_path=path)
+        self.out['phase'] = Phase.COMPUTATION
+
+    def _device_broadcast(self, rt, path):
+        """C5 on the device transports: only the pre-training site reads its checkpoint; parameters, buffers and
+        optimizer moments then go GPU-to-GPU over NVLink peer copies (``DistArena.broadcast_from``) instead of S-1
+        file reads + H2D copies (ref remote.py:205-215 / local.py:208-212).  False -> caller takes the file path."""
+        import torch.distributed as _dist
+        transport = self.cache.get('transport', Transport.FILE)
+        src_site = self.input.get('pretrained_site')
+        if transport not in (Transport.NVLINK, Transport.NCCL) or src_site is None:
+            return False
+        if not (_dist.is_available() and _dist.is_initialized() and _dist.get_world_size() > 1):
+            return False
+        learner = self._get_learner_cls(rt.learner_cls)(trainer=rt.trainer, mp_pool=rt.mp_pool)
+        arena = getattr(learner, 'arena', None)
+        if arena is None or not hasattr(arena, 'broadcast_from'):
+            return False
+        mine = self.state['clientId'] == src_site
+        if mine:
+            rt.trainer.load_checkpoint(file_path=path)
+        arena.broadcast_from(is_source=mine, model=learner.model)
+        self.out['weights_broadcast'] = 'device'
+        return True
+
+    _ENTRY = {Phase.INIT_RUNS: '_enter_init_runs', Phase.NEXT_RUN: '_enter_next_run',
+              Phase.PRE_COMPUTATION: '_enter_pre_computation'}
+    _EXIT = {Phase.COMPUTATION: '_computation_round', Phase.SUCCESS: '_collect_results'}
+
     def compute(self, mp_pool, trainer_cls, dataset_cls=None, datahandle_cls=_DataHandle,
                 learner_cls=_dSGDLearner, **kw):
-        trainer = trainer_cls(data_handle=datahandle_cls(
+        rt = _Round(mp_pool=mp_pool, trainer_cls=trainer_cls, dataset_cls=dataset_cls, datahandle_cls=datahandle_cls,
+                    learner_cls=learner_cls)
+        rt.trainer = trainer_cls(data_handle=datahandle_cls(
             cache=self.cache, input=self.input, state=self.state, dataloader_args=self._dataloader_args))
+        self.out['phase'] = self.input.get('phase', Phase.INIT_RUNS)
+        self._dispatch(self._ENTRY, self.out['phase'], rt)
+        rt.learner = self._get_learner_cls(learner_cls)(trainer=rt.trainer, mp_pool=mp_pool)
+        rt.modes = list(rt.learner.global_modes.values())
+        self.out['mode'] = rt.learner.global_modes.get(self.state['clientId'], self.cache['mode'])
+        self._dispatch(self._EXIT, self.out['phase'], rt)
 
-        phase = self.out['phase'] = self.input.get('phase', Phase.INIT_RUNS)
-        if phase == Phase.INIT_RUNS:
-            self.out.update(**self._init_runs(trainer))
-            # share the constructor-level arguments with the aggregator and freeze them
-            shared = {k: self.cache[k] for k in self._args}
-            # also share what the aggregator needs to build the same metric objects
-            for k in ('num_class', *self.cache.get('shared_keys', ())):
-                if k in self.cache and k not in shared:
-                    shared[k] = self.cache[k]
-            self.cache['frozen_args'] = _FrozenDict(shared)
-            self.out['shared_args'] = self.cache['frozen_args']
+    def _dispatch(self, table, key, rt):
+        name = table.get(key)
+        if name is not None:
+            getattr(self, name)(rt)
 
-        elif phase == Phase.NEXT_RUN:
-            self.cache.update(**self.input['global_runs'][self.state['clientId']])
-            self.out.update(**self._next_run(trainer))
-            if self.cache['mode'] == Mode.TRAIN:
-                self.out.update(**self._pretrain_local(
-                    trainer_cls, datahandle_cls,
-                    trainer.data_handle.get_train_dataset(dataset_cls),
-                    trainer.data_handle.get_validation_dataset(dataset_cls)))
+    # ---- computation-phase rules: (guard, action), evaluated in order, all that match fire ----
+    def _do_save_best(self, rt):
+        self._sync_optimizer_state()
+        rt.trainer.save_checkpoint(file_path=self.cache['log_dir'] + _sep + self.cache['best_nn_state'])
 
-        elif phase == Phase.PRE_COMPUTATION and self.input.get('pretrained_weights'):
-            trainer.load_checkpoint(file_path=self.state['baseDirectory'] + _sep + self.input['pretrained_weights'])
-            self.out['phase'] = Phase.COMPUTATION
+    def _do_update(self, rt):
+        self.out.update(**rt.learner.step())
 
-        learner = self._get_learner_cls(learner_cls)(trainer=trainer, mp_pool=mp_pool)
-        self.out['mode'] = learner.global_modes.get(self.state['clientId'], self.cache['mode'])
+    def _do_train(self, rt):
+        # Lagging sites re-shuffle and keep contributing until *everyone* is waiting.
+        it, out = rt.learner.to_reduce()
+        self.out.update(**out)
+        if it.get('averages') and it.get('metrics'):
+            self.cache[Key.TRAIN_SERIALIZABLE].append(
+                {'averages': it['averages'].serialize(), 'metrics': it['metrics'].serialize()})
+            self.out.update(**rt.trainer.on_iteration_end(0, 0, it))
 
-        if self.out['phase'] == Phase.COMPUTATION:
-            self._computation_round(trainer, learner, dataset_cls)
-        elif self.out['phase'] == Phase.SUCCESS:
-            self._collect_results()
+    def _do_validate(self, rt):
+        self.out.update(**rt.trainer.validation_distributed(rt.dataset_cls))
+        self.out[Key.TRAIN_SERIALIZABLE] = self.cache[Key.TRAIN_SERIALIZABLE]
+        self.cache[Key.TRAIN_SERIALIZABLE] = []
+        self.out['mode'] = Mode.TRAIN_WAITING
 
-    def _computation_round(self, trainer, learner, dataset_cls):
-        modes = list(learner.global_modes.values())
-        if self.input.get('save_current_as_best'):
-            self._sync_optimizer_state()
-            learner.trainer.save_checkpoint(file_path=self.cache['log_dir'] + _sep + self.cache['best_nn_state'])
+    def _do_test(self, rt):
+        self.out.update(**rt.trainer.test_distributed(rt.dataset_cls))
+        self.out['mode'] = self.cache['frozen_args']['mode']
+        self.out['phase'] = Phase.NEXT_RUN_WAITING
+        self._sync_optimizer_state()
+        rt.trainer.save_checkpoint(file_path=self.cache['log_dir'] + _sep + self.cache['latest_nn_state'])
+        _utils.save_cache(self.cache, self.cache['log_dir'])
 
-        if self.input.get('update'):
-            self.out.update(**learner.step())
+    _COMPUTATION_RULES = (
+        (lambda self, rt: bool(self.input.get('save_current_as_best')), '_do_save_best'),
+        (lambda self, rt: bool(self.input.get('update')), '_do_update'),
+        (lambda self, rt: any(m == Mode.TRAIN for m in rt.modes), '_do_train'),
+        (lambda self, rt: bool(rt.modes) and all(m == Mode.VALIDATION for m in rt.modes), '_do_validate'),
+        (lambda self, rt: bool(rt.modes) and all(m == Mode.TEST for m in rt.modes), '_do_test'),
+    )
 
-        if any(m == Mode.TRAIN for m in modes):
-            # Lagging sites re-shuffle and keep contributing until *everyone* is waiting.
-            it, out = learner.to_reduce()
-            self.out.update(**out)
-            if it.get('averages') and it.get('metrics'):
-                self.cache[Key.TRAIN_SERIALIZABLE].append(
-                    {'averages': it['averages'].serialize(), 'metrics': it['metrics'].serialize()})
-                self.out.update(**trainer.on_iteration_end(0, 0, it))
-
-        if modes and all(m == Mode.VALIDATION for m in modes):
-            self.out.update(**trainer.validation_distributed(dataset_cls))
-            self.out[Key.TRAIN_SERIALIZABLE] = self.cache[Key.TRAIN_SERIALIZABLE]
-            self.cache[Key.TRAIN_SERIALIZABLE] = []
-            self.out['mode'] = Mode.TRAIN_WAITING
-
-        if modes and all(m == Mode.TEST for m in modes):
-            self.out.update(**trainer.test_distributed(dataset_cls))
-            self.out['mode'] = self.cache['frozen_args']['mode']
-            self.out['phase'] = Phase.NEXT_RUN_WAITING
-            self._sync_optimizer_state()
-            trainer.save_checkpoint(file_path=self.cache['log_dir'] + _sep + self.cache['latest_nn_state'])
-            _utils.save_cache(self.cache, self.cache['log_dir'])
+    def _computation_round(self, rt):
+        for guard, action in self._COMPUTATION_RULES:
+            if guard(self, rt):
+                getattr(self, action)(rt)
 
     def _sync_optimizer_state(self):
         """Sharded (two-shot / NVLS) optimizer moments are collected before a global checkpoint;
@@ -224,7 +285,7 @@ class COINNLocal:
         if arena is not None:
             arena.gather_state()
 
-    def _collect_results(self):
+    def _collect_results(self, rt=None):
         """Final round: pick up the results zip broadcast by the aggregator (retry x3)."""
         name = f"{self.input['results_zip']}.zip"
         src = f"{self.state['baseDirectory']}{_sep}{name}"

@@ -59,6 +59,13 @@ def check(logic, k, v, kw):
     return logic([site_vars.get(k) == v for site_vars in kw.values()])
 
 
+class _AggRound:
+    __slots__ = ('mp_pool', 'reducer_cls', 'trainer', 'reducer')
+
+    def __init__(self, mp_pool, reducer_cls, trainer):
+        self.mp_pool, self.reducer_cls, self.trainer, self.reducer = mp_pool, reducer_cls, trainer, None
+
+
 class COINNRemote:
     def __init__(self, cache: dict = None, input: dict = None, state: dict = None, verbose=False, **kw):
         self.out = {}
@@ -199,52 +206,78 @@ class COINNRemote:
             if sv.get('weights_file') is not None:
                 src = self.state['baseDirectory'] + _os.sep + site + _os.sep + sv['weights_file']
                 out['pretrained_weights'] = f'pretrained_{_conf.weights_file}'
+                out['pretrained_site'] = site            # device transports broadcast GPU-to-GPU from this site (C5)
                 _shutil.copy(src, self.state['transferDirectory'] + _os.sep + out['pretrained_weights'])
                 break
         return out
 
     # ------------------------------------------------------------------ compute
-    def compute(self, mp_pool, trainer_cls, reducer_cls: callable = _dSGDReducer, **kw):
-        trainer = trainer_cls(data_handle=EmptyDataHandle(cache=self.cache, input=self.input, state=self.state))
-        self.out['phase'] = self.input.get('phase', Phase.INIT_RUNS)
+    # The aggregator is a barrier table: every row is (key, value, handler); a row fires when ALL sites report
+    # ``site[key] == value`` (the protocol's global barrier, ``check``).  Rows are evaluated top to bottom within a
+    # round; the computation rows are nested under the row that recognises the computation phase.
+    def _on_all_init(self, rt):
+        self._init_runs()
+        self._start_next_fold_or_finish(rt)
 
-        if check(all, 'phase', Phase.INIT_RUNS, self.input):
-            self._init_runs()
-            if len(self.cache['folds']) > 0:
-                self.out['global_runs'] = self._next_run(trainer)
-                self.out['phase'] = Phase.NEXT_RUN
-            else:                                   # resumed run with nothing left to train
-                self.out.update(**self._send_global_scores(trainer))
-                self.out['phase'] = Phase.SUCCESS
+    def _on_all_pre_computation(self, rt):
+        self.out.update(**self._pre_compute())
+        self.out['phase'] = Phase.PRE_COMPUTATION
 
-        if check(all, 'phase', Phase.PRE_COMPUTATION, self.input):
-            self.out.update(**self._pre_compute())
-            self.out['phase'] = Phase.PRE_COMPUTATION
+    def _on_all_computation(self, rt):
+        rt.reducer = self._get_reducer_cls(rt.reducer_cls)(trainer=rt.trainer, mp_pool=rt.mp_pool)
+        self.out['phase'] = Phase.COMPUTATION
+        self._fire(self._COMPUTATION_BARRIERS, rt)
 
+    def _on_all_reduce(self, rt):
+        self.out.update(**rt.reducer.reduce())
+
+    def _on_all_validation_waiting(self, rt):
+        self.cache['epoch'] += 1
+        validate = self.cache['epoch'] % self.cache['validation_epochs'] == 0
+        self.out['global_modes'] = self._set_mode(mode=Mode.VALIDATION if validate else Mode.TRAIN)
+
+    def _on_all_train_waiting(self, rt):
+        info = self._on_epoch_end(rt.reducer)
+        self.out['global_modes'] = self._set_mode(mode=self._next_epoch(**info)['mode'])
+
+    def _on_all_next_run_waiting(self, rt):
+        self._on_run_end(rt.trainer)
+        self._start_next_fold_or_finish(rt)
+
+    def _start_next_fold_or_finish(self, rt):
+        if len(self.cache['folds']) > 0:
+            self.out['global_runs'] = self._next_run(rt.trainer)
+            self.out['phase'] = Phase.NEXT_RUN
+        else:                                       # also: a resumed run with nothing left to train
+            self.out.update(**self._send_global_scores(rt.trainer))
+            self.out['phase'] = Phase.SUCCESS
+
+    def _echo_modes(self, rt):
         self.out['global_modes'] = self._set_mode()
-        if check(all, 'phase', Phase.COMPUTATION, self.input):
-            reducer = self._get_reducer_cls(reducer_cls)(trainer=trainer, mp_pool=mp_pool)
-            self.out['phase'] = Phase.COMPUTATION
-            if check(all, 'reduce', True, self.input):
-                self.out.update(**reducer.reduce())
 
-            if check(all, 'mode', Mode.VALIDATION_WAITING, self.input):
-                self.cache['epoch'] += 1
-                validate = self.cache['epoch'] % self.cache['validation_epochs'] == 0
-                self.out['global_modes'] = self._set_mode(mode=Mode.VALIDATION if validate else Mode.TRAIN)
+    _BARRIERS = (
+        ('phase', Phase.INIT_RUNS, '_on_all_init'),
+        ('phase', Phase.PRE_COMPUTATION, '_on_all_pre_computation'),
+        (None, None, '_echo_modes'),                                   # unconditional: default mode echo
+        ('phase', Phase.COMPUTATION, '_on_all_computation'),
+        ('phase', Phase.NEXT_RUN_WAITING, '_on_all_next_run_waiting'),
+    )
+    _COMPUTATION_BARRIERS = (
+        ('reduce', True, '_on_all_reduce'),
+        ('mode', Mode.VALIDATION_WAITING, '_on_all_validation_waiting'),
+        ('mode', Mode.TRAIN_WAITING, '_on_all_train_waiting'),
+    )
 
-            if check(all, 'mode', Mode.TRAIN_WAITING, self.input):
-                info = self._on_epoch_end(reducer)
-                self.out['global_modes'] = self._set_mode(mode=self._next_epoch(**info)['mode'])
+    def _fire(self, table, rt):
+        for key, value, handler in table:
+            if key is None or check(all, key, value, self.input):
+                getattr(self, handler)(rt)
 
-        if check(all, 'phase', Phase.NEXT_RUN_WAITING, self.input):
-            self._on_run_end(trainer)
-            if len(self.cache['folds']) > 0:
-                self.out['global_runs'] = self._next_run(trainer)
-                self.out['phase'] = Phase.NEXT_RUN
-            else:
-                self.out.update(**self._send_global_scores(trainer))
-                self.out['phase'] = Phase.SUCCESS
+    def compute(self, mp_pool, trainer_cls, reducer_cls: callable = _dSGDReducer, **kw):
+        rt = _AggRound(mp_pool, reducer_cls,
+                       trainer_cls(data_handle=EmptyDataHandle(cache=self.cache, input=self.input, state=self.state)))
+        self.out['phase'] = self.input.get('phase', Phase.INIT_RUNS)
+        self._fire(self._BARRIERS, rt)
 
     def _next_epoch(self, **kw):
         # NB ``>`` (not ``>=``): the reference trains epochs+1 epochs (quirk §8.5-5) - kept for parity

@@ -235,6 +235,78 @@ class DistArena:
                     _dist.broadcast(buf[lo:hi], src=src, group=self.group)
         self._publish_state_views()
 
+    # --------------------------------------------------------------- C5: device-to-device broadcast
+    def broadcast_from(self, is_source, model=None):
+        """Make every site a copy of the one site with ``is_source=True``: fp32 master parameters, optimizer moments,
+        step counter and (optionally) the float buffers of ``model`` (BatchNorm running statistics).  On the NVLink
+        backend the bulk moves as peer-to-peer copies out of the source's symmetric buffers (parameter arena directly;
+        moments / buffers staged through the gradient arena, which is idle and zero between steps) - no file, no host
+        bounce, no NCCL on the payload.  Other backends use ``torch.distributed.broadcast``."""
+        if self.world == 1:
+            return 0
+        dev = self.device if self.device.type == 'cuda' else _torch.device('cpu')
+        who = _torch.tensor([self.rank if is_source else -1], dtype=_torch.int64, device=dev)
+        _dist.all_reduce(who, op=_dist.ReduceOp.MAX, group=self.group)
+        src = int(who.item())
+        if src < 0:
+            raise RuntimeError('broadcast_from: no site declared itself the source')
+        gsrc = _dist.get_global_rank(self.group, src) if self.group is not None else src
+        bufs = [b for b in (model.buffers() if model is not None else []) if b.is_floating_point()]
+        ints = [b for b in (model.buffers() if model is not None else []) if not b.is_floating_point()]
+        symmetric = self.backend == 'nvlink' and isinstance(self.param_buf, SymmetricBuffer)
+        staging = self.grad_buf if (symmetric and isinstance(self.grad_buf, SymmetricBuffer)) else None
+
+        def sync():
+            _torch.cuda.synchronize(self.device)
+            self.param_buf.barrier()
+
+        with _torch.no_grad():
+            if symmetric:
+                sync()                                           # the source has finished loading its checkpoint
+                if self.rank != src:
+                    self.flat_param.copy_(self.param_buf.peer_tensor(src))
+                sync()
+            else:
+                _dist.broadcast(self.flat_param, src=gsrc, group=self.group)
+            payload = [self.m, self.v] if self.backend != 'torch' else []
+            if bufs:
+                flat_b = _torch.cat([b.detach().reshape(-1).float() for b in bufs])
+                payload.append(flat_b)
+            for t in payload:
+                n = t.numel()
+                if staging is not None and n <= staging.numel:
+                    if self.rank == src:
+                        staging.local[:n].copy_(t)
+                    sync()
+                    if self.rank != src:
+                        t.copy_(staging.peer_tensor(src)[:n])
+                    sync()
+                    if self.rank == src:
+                        staging.local[:n].zero_()                # the gradient arena must be zero when a step starts
+                else:
+                    _dist.broadcast(t, src=gsrc, group=self.group)
+            if bufs:
+                off = 0
+                for b in bufs:
+                    b.copy_(flat_b[off:off + b.numel()].view_as(b).to(b.dtype))
+                    off += b.numel()
+            for b in ints:
+                _dist.broadcast(b, src=gsrc, group=self.group)
+            if self.backend != 'torch':
+                _dist.broadcast(self.step_count, src=gsrc, group=self.group)
+                self.host_step = int(self.step_count.item())
+            if self.shadow_buf is not None:
+                self.shadow_buf.local.copy_(self.flat_param)
+            if symmetric:
+                sync()
+        self._publish_state_views()
+        if self.backend == 'torch':          # CPU / exotic optimizers: ship the torch optimizer state as an object
+            box = [self.optimizer.state_dict() if self.rank == src else None]
+            _dist.broadcast_object_list(box, src=gsrc, group=self.group)
+            if self.rank != src:
+                self.optimizer.load_state_dict(box[0])
+        return src
+
     # ------------------------------------------------------------------------------- the step
     def _pick_variant(self, nbytes):
         v = self.variant

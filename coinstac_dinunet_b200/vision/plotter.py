@@ -23,6 +23,8 @@ def _pyplot():
             import matplotlib
             matplotlib.use('agg')
             import matplotlib.pyplot as plt
+            if not hasattr(plt, 'subplots'):      # a stub module (e.g. installed by a harness): treat as absent
+                raise ImportError('matplotlib.pyplot has no subplots')
             plt.rcParams['figure.figsize'] = [16, 9]
             _plt = plt
         except Exception:
