@@ -209,7 +209,7 @@ class COINNLocal:
         if mine:
             rt.trainer.load_checkpoint(file_path=path)
         arena.broadcast_from(is_source=mine, model=learner.model)
-        self.out['weights_broadcast'] = 'device'
+        self.out['weights_broadcast'] = self.cache['_weights_broadcast'] = 'device'
         return True
 
     _ENTRY = {Phase.INIT_RUNS: '_enter_init_runs', Phase.NEXT_RUN: '_enter_next_run',

@@ -28,7 +28,8 @@ def scenario_protocol(work, opts):
     eng = DistEngine(work, inputspec=spec)
     sizes = [24, 18, 30, 12, 20, 16, 28, 22]
     write_synthetic_site(eng.state['baseDirectory'], sizes[eng.rank % len(sizes)], (66,), seed=eng.rank)
-    rounds = eng.run_nodes(FSVTrainer, FSVDataset, max_rounds=500)
+    local_kw = {'pretrain_args': {'epochs': 2}} if opts.get('pretrain') == '1' else None
+    rounds = eng.run_nodes(FSVTrainer, FSVDataset, local_kw=local_kw, max_rounds=500)
     model = eng.cache['nn']['fs_net']
     flat = torch.cat([p.detach().float().reshape(-1).cpu() for p in model.parameters()])
     gathered = [None] * eng.world
@@ -39,7 +40,7 @@ def scenario_protocol(work, opts):
         res = {'rounds': rounds, 'replicas_identical': bool(same), 'csv': os.path.exists(csv),
                'backend': eng.cache['_arena'].backend, 'fused_steps': eng.cache['_arena'].steps_done,
                'graphed': '_graph_step' in eng.cache, 'param_sum': float(gathered[0].double().sum()),
-               'trace': [t['remote'] for t in eng.trace]}
+               'trace': [t['remote'] for t in eng.trace], 'weights_broadcast': eng.cache.get('_weights_broadcast')}
         with open(os.path.join(work, 'result.json'), 'w') as fp:
             json.dump(res, fp)
 

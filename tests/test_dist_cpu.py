@@ -28,3 +28,13 @@ def test_dist_engine_two_sites(tmp_path, engine, port):
     assert res['csv'] and res['trace'][-2] == 'success'
     assert res['replicas_identical']
     assert res['backend'] == 'torch' and res['fused_steps'] > 0
+
+
+def test_pretrained_weights_broadcast_without_files_on_device_transports(tmp_path):
+    """C5: on the nvlink / nccl transports only the pre-training site reads its checkpoint; the other sites receive
+    parameters, buffers and optimizer state through DistArena.broadcast_from (gloo stand-in here, NVLink peer copies on
+    GPUs) and all replicas stay identical through the rest of the run."""
+    res = run_workers('protocol', tmp_path, port=29614, extra=['agg_engine=dSGD', 'pretrain=1'])
+    assert res['csv'] and res['trace'][-2] == 'success' and res['replicas_identical']
+    assert 'pre_computation' in [str(t).split('.')[-1].lower() for t in res['trace']]
+    assert res['weights_broadcast'] == 'device'
