@@ -73,11 +73,11 @@ class VBMNet(_nn.Module):
 
     def _forward_native(self, x):
         from ..ops.linear import linear as _linear
-        from ..ops.vbm import ConvBnReluPoolFn, conv1_fused_enabled
+        from ..ops.vbm import ConvBnReluPoolFn
         h = x[:, 0] if x.dim() == 5 else x                     # [N, D, H, W]; C_in == 1
-        if h.dtype != _torch.float32 and not (conv1_fused_enabled() and h.dtype == _torch.bfloat16):
-            h = h.float()                                       # stored-y path: one 100 MB cast, then fp32 taps
-        # (the fused first block re-lays the volume out as a padded bf16 matrix anyway: bf16 host volumes go in as is)
+        if h.dtype not in (_torch.float32, _torch.bfloat16):
+            h = h.float()
+        # (the fused first block re-lays the volume out as a padded bf16 matrix: fp32 and bf16 volumes go in as they are)
         for blk in self.blocks:
             bn = blk.bn
             h = ConvBnReluPoolFn.apply(h, blk.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,

@@ -565,8 +565,15 @@ static int c1f_launch(const void* xp, C1FParams& p, int N, int D, int H, int W, 
 
 }  // namespace coinn
 
+// rows and row length (elements) of the padded bf16 input matrix for an [N, D, H, W] volume:
+// (D+2)*(H+2) rows per sample, W rounded up to whole 8-element chunks plus one zero chunk
+COINN_API int coinn_conv1_padded_shape(int N, int D, int H, int W, long long* rows, int* cols) {
+    *rows = (long long)N * (D + 2) * (H + 2);
+    *cols = 8 * ((W + 7) / 8 + 1);
+    return 0;
+}
+
 // x: [N,D,H,W] fp32 (x_dtype 0) or bf16 (1)  ->  xp: [N*(H+2)*(D+2), Wq] bf16, zero halo, d' fastest
-// (row count / length: coinn_conv1_padded_shape)
 COINN_API int coinn_conv1_pad_input_hd(const void* x, int x_dtype, void* xp, int N, int D, int H, int W, void* stream) {
     using namespace coinn;
     const int Dp = D + 2, Hp = H + 2, chunks = (W + 7) / 8 + 1;

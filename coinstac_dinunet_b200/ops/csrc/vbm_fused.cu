@@ -2,13 +2,11 @@
 // activations, everything elementwise/normalisation/pooling folded into as few passes over HBM as
 // training-mode BatchNorm allows.
 //
-//   conv1_fwd_kernel          Conv3d(1 -> 16, k3 p1) on CUDA cores (K = 27 is tensor-core hostile) + per-channel
-//                             sum / sum-of-squares in the same pass (BatchNorm batch statistics)
+//   (the first block, C_in = 1, lives in conv1_fused.cu: conv recomputed on tcgen05, nothing stored at full resolution)
 //   bn_stats_kernel           sum / sumsq of a [M, C] bf16 tensor (statistics for the tcgen05 conv outputs)
 //   bn_relu_pool_fwd_kernel   y -> maxpool2(relu(bn(y)))  : reads y once, writes 1/8 of it
 //   bn_relu_pool_bwd_stats    dgamma, dbeta of the fused block from (y, dpooled)  [pass A]
 //   bn_relu_pool_bwd_apply    dy of the fused block (full resolution)              [pass B]
-//   conv1_wgrad_kernel        dW1[16,27] = sum_vox dy[vox,:] (x) x[vox + tap]
 //
 // The PyTorch chain for one block (conv -> BN -> ReLU -> MaxPool, autocast bf16) moves ~10x the bytes of this.
 #include "common.cuh"
@@ -25,115 +23,6 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-}
-
-// ------------------------------------------------------------------------------------------------
-// conv1: x [N,D,H,W] (fp32 or bf16, single channel) -> y [N,D,H,W,16] bf16, + stats[0:16]=sum, [16:32]=sumsq
-// Each thread produces VOX consecutive-w output voxels x 16 channels, weights broadcast from shared memory.
-// ------------------------------------------------------------------------------------------------
-constexpr int C1_OUT = 16;
-constexpr int C1_VOX = 4;
-
-template <typename TIn>
-__device__ __forceinline__ float load_in(const TIn* p);
-template <> __device__ __forceinline__ float load_in<float>(const float* p) { return __ldg(p); }
-template <> __device__ __forceinline__ float load_in<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
-
-template <typename TIn>
-__global__ void __launch_bounds__(256, 1) conv1_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ w /*[16][27]*/,
-                                                        __nv_bfloat16* __restrict__ y, float* __restrict__ stats, Dims d) {
-    __shared__ float4 ws[27][4];              // [tap][co/4] -> 4 consecutive output channels
-    __shared__ float red[2 * C1_OUT];
-    for (int i = threadIdx.x; i < 27 * C1_OUT; i += blockDim.x) {
-        const int tap = i / C1_OUT, co = i % C1_OUT;
-        reinterpret_cast<float*>(&ws[tap][0])[co] = w[co * 27 + tap];
-    }
-    if (threadIdx.x < 2 * C1_OUT) red[threadIdx.x] = 0.f;
-    __syncthreads();
-
-    const int wgroups = (d.W + C1_VOX - 1) / C1_VOX;
-    const long long total = (long long)d.N * d.D * d.H * wgroups;
-    float s1[C1_OUT], s2[C1_OUT];
-#pragma unroll
-    for (int c = 0; c < C1_OUT; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
-
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
-        const int wg = (int)(g % wgroups);
-        long long t = g / wgroups;
-        const int h = (int)(t % d.H); t /= d.H;
-        const int dd = (int)(t % d.D);
-        const int n = (int)(t / d.D);
-        const int w0 = wg * C1_VOX;
-
-        float acc[C1_VOX][C1_OUT];
-#pragma unroll
-        for (int v = 0; v < C1_VOX; ++v)
-#pragma unroll
-            for (int c = 0; c < C1_OUT; ++c) acc[v][c] = 0.f;
-
-        // all 9 x (VOX+2) neighbourhood values first (branch-free: clamped address x validity), so the loads
-        // are in flight together and the 27 x 64 FMAs below run without further memory stalls
-        float in[9][C1_VOX + 2];
-#pragma unroll
-        for (int r = 0; r < 9; ++r) {
-            const int zd = dd + r / 3 - 1, zh = h + r % 3 - 1;
-            const bool row_ok = zd >= 0 && zd < d.D && zh >= 0 && zh < d.H;
-            const int cd = min(max(zd, 0), d.D - 1), chh = min(max(zh, 0), d.H - 1);
-            const TIn* row = x + (((long long)n * d.D + cd) * d.H + chh) * d.W;
-#pragma unroll
-            for (int j = 0; j < C1_VOX + 2; ++j) {
-                const int zw = w0 + j - 1;
-                const int cw = min(max(zw, 0), d.W - 1);
-                const float v = load_in<TIn>(row + cw);
-                in[r][j] = (row_ok && zw >= 0 && zw < d.W) ? v : 0.f;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 9; ++r) {
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int tap = r * 3 + kw;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 wv = ws[tap][q];
-#pragma unroll
-                    for (int v = 0; v < C1_VOX; ++v) {
-                        const float xv = in[r][v + kw];
-                        acc[v][4 * q + 0] = fmaf(xv, wv.x, acc[v][4 * q + 0]);
-                        acc[v][4 * q + 1] = fmaf(xv, wv.y, acc[v][4 * q + 1]);
-                        acc[v][4 * q + 2] = fmaf(xv, wv.z, acc[v][4 * q + 2]);
-                        acc[v][4 * q + 3] = fmaf(xv, wv.w, acc[v][4 * q + 3]);
-                    }
-                }
-            }
-        }
-        __nv_bfloat16* out = y + ((((long long)n * d.D + dd) * d.H + h) * d.W + w0) * C1_OUT;
-#pragma unroll
-        for (int v = 0; v < C1_VOX; ++v) {
-            if (w0 + v >= d.W) break;
-            float r[8], r2[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) { r[c] = acc[v][c]; r2[c] = acc[v][8 + c]; }
-            const uint4 lo = pack8(r), hi = pack8(r2);
-            // statistics of the *stored* (bf16-rounded) values: exactly what BatchNorm normalises later
-            float q[8];
-            unpack8(lo, q);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) { s1[c] += q[c]; s2[c] = fmaf(q[c], q[c], s2[c]); }
-            unpack8(hi, q);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) { s1[8 + c] += q[c]; s2[8 + c] = fmaf(q[c], q[c], s2[8 + c]); }
-            reinterpret_cast<uint4*>(out + v * C1_OUT)[0] = lo;
-            reinterpret_cast<uint4*>(out + v * C1_OUT)[1] = hi;
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < C1_OUT; ++c) {
-        const float a = warp_sum(s1[c]), b = warp_sum(s2[c]);
-        if (lane_id() == 0) { atomicAdd(&red[c], a); atomicAdd(&red[C1_OUT + c], b); }
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * C1_OUT) atomicAdd(&stats[threadIdx.x], red[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -509,82 +398,6 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_stats_pooled_kernel(const __n
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv1 wgrad: dW[co, tap] += sum_vox dy[vox, co] * x[vox + tap]      (dy: [N,D,H,W,16] bf16, x: [N,D,H,W])
-// lane = tap (27 of 32 lanes active), 16 output channels in registers, dy row broadcast from shared memory.
-// ------------------------------------------------------------------------------------------------
-constexpr int WG_TILE_W = 64;            // voxels (along w) staged per step
-
-template <typename TIn>
-__global__ void __launch_bounds__(128) conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x,
-                                                          float* __restrict__ dw /*[16][27]*/, Dims d) {
-    __shared__ __align__(16) float s_dy[4][WG_TILE_W][C1_OUT];             // per warp, already fp32
-    __shared__ float s_x[4][3][3][WG_TILE_W + 2];                          // per warp: halo rows
-    __shared__ float s_acc[C1_OUT * 27];
-    for (int i = threadIdx.x; i < C1_OUT * 27; i += blockDim.x) s_acc[i] = 0.f;
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int nwarps = blockDim.x >> 5;
-    const int wtiles = (d.W + WG_TILE_W - 1) / WG_TILE_W;
-    const long long total = (long long)d.N * d.D * d.H * wtiles;
-    const int tap = lane < 27 ? lane : 26;
-    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-    float acc[C1_OUT];
-#pragma unroll
-    for (int c = 0; c < C1_OUT; ++c) acc[c] = 0.f;
-
-    for (long long job = (long long)blockIdx.x * nwarps + warp; job < total; job += (long long)gridDim.x * nwarps) {
-        const int wt = (int)(job % wtiles);
-        long long t = job / wtiles;
-        const int h = (int)(t % d.H); t /= d.H;
-        const int dd = (int)(t % d.D);
-        const int n = (int)(t / d.D);
-        const int w0 = wt * WG_TILE_W;
-        const int nw = min(WG_TILE_W, d.W - w0);
-        __syncwarp();
-        // stage dy rows (nw voxels x 16 ch) as fp32 and the 3x3 halo rows of x
-        const uint4* src = reinterpret_cast<const uint4*>(dy + ((((long long)n * d.D + dd) * d.H + h) * d.W + w0) * C1_OUT);
-        for (int i = lane; i < nw * 2; i += 32) {
-            float f[8];
-            unpack8(ld_stream_u4(src + i), f);
-            float4* dst = reinterpret_cast<float4*>(&s_dy[warp][0][0]) + i * 2;
-            dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-            dst[1] = make_float4(f[4], f[5], f[6], f[7]);
-        }
-        for (int r = 0; r < 9; ++r) {
-            const int zd = dd + r / 3 - 1, zh = h + r % 3 - 1;
-            const bool ok = zd >= 0 && zd < d.D && zh >= 0 && zh < d.H;
-            const TIn* row = x + (((long long)n * d.D + (ok ? zd : 0)) * d.H + (ok ? zh : 0)) * d.W;
-            for (int j = lane; j < nw + 2; j += 32) {
-                const int zw = w0 + j - 1;
-                s_x[warp][r / 3][r % 3][j] = (ok && zw >= 0 && zw < d.W) ? load_in<TIn>(row + zw) : 0.f;
-            }
-        }
-        __syncwarp();
-        const float* xs = &s_x[warp][kd][kh][kw];
-#pragma unroll 4
-        for (int v = 0; v < nw; ++v) {
-            const float xv = xs[v];
-            const float4* g = reinterpret_cast<const float4*>(&s_dy[warp][v][0]);   // same address for all lanes: broadcast
-            const float4 g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3];
-            acc[0] = fmaf(g0.x, xv, acc[0]);   acc[1] = fmaf(g0.y, xv, acc[1]);
-            acc[2] = fmaf(g0.z, xv, acc[2]);   acc[3] = fmaf(g0.w, xv, acc[3]);
-            acc[4] = fmaf(g1.x, xv, acc[4]);   acc[5] = fmaf(g1.y, xv, acc[5]);
-            acc[6] = fmaf(g1.z, xv, acc[6]);   acc[7] = fmaf(g1.w, xv, acc[7]);
-            acc[8] = fmaf(g2.x, xv, acc[8]);   acc[9] = fmaf(g2.y, xv, acc[9]);
-            acc[10] = fmaf(g2.z, xv, acc[10]); acc[11] = fmaf(g2.w, xv, acc[11]);
-            acc[12] = fmaf(g3.x, xv, acc[12]); acc[13] = fmaf(g3.y, xv, acc[13]);
-            acc[14] = fmaf(g3.z, xv, acc[14]); acc[15] = fmaf(g3.w, xv, acc[15]);
-        }
-    }
-    if (lane < 27) {
-#pragma unroll
-        for (int c = 0; c < C1_OUT; ++c) atomicAdd(&s_acc[c * 27 + lane], acc[c]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < C1_OUT * 27; i += blockDim.x) atomicAdd(&dw[i], s_acc[i]);
-}
-
-// ------------------------------------------------------------------------------------------------
 // One launch packs a conv weight [COUT, CIN, 27] (fp32) into both bf16 GEMM operands:
 //   wf[co, tap*CIN + ci]          (fprop:  y  = conv(x,  W))
 //   wd[ci, (26-tap)*COUT + co]    (dgrad:  dx = conv(dy, flip(W)^T))
@@ -611,19 +424,6 @@ static inline int grid_for(long long work_items, int threads, int per_thread = 4
 
 using coinn::Dims;
 
-// x_dtype: 0 fp32, 1 bf16.  stats must be zeroed (2*16 floats).
-COINN_API int coinn_conv1_fwd(const void* x, int x_dtype, const float* w, void* y, float* stats,
-                              int N, int D, int H, int W, void* stream) {
-    using namespace coinn;
-    Dims d{N, D, H, W};
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const long long groups = (long long)N * D * H * ((W + C1_VOX - 1) / C1_VOX);
-    const int grid = grid_for(groups, 256, 2);
-    if (x_dtype != 0) return (int)cudaErrorInvalidValue;       // callers up-cast bf16 volumes (8.5 MB) first
-    conv1_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, w, (__nv_bfloat16*)y, stats, d);
-    COINN_CHECK_LAUNCH();
-    return 0;
-}
 
 COINN_API int coinn_bn_stats(const void* y, float* stats, long long M, int C, void* stream) {
     using namespace coinn;
@@ -770,19 +570,6 @@ COINN_API int coinn_bn_pool_bwd_stats_pooled(const void* p, const void* dp, cons
     return 0;
 }
 
-// dw[16*27] must be zeroed.
-COINN_API int coinn_conv1_wgrad(const void* dy, const void* x, int x_dtype, float* dw, int N, int D, int H, int W, void* stream) {
-    using namespace coinn;
-    Dims d{N, D, H, W};
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const long long jobs = (long long)N * D * H * ((W + WG_TILE_W - 1) / WG_TILE_W);
-    long long want = (jobs + 4 * 4 - 1) / (4 * 4);
-    const int grid = (int)(want < 1 ? 1 : (want > 8LL * B200_SM_COUNT ? 8LL * B200_SM_COUNT : want));
-    if (x_dtype == 0) conv1_wgrad_kernel<float><<<grid, 128, 0, st>>>((const __nv_bfloat16*)dy, (const float*)x, dw, d);
-    else conv1_wgrad_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, d);
-    COINN_CHECK_LAUNCH();
-    return 0;
-}
 
 COINN_API int coinn_pack_conv_weights(const float* w, void* wf, void* wd, int cout, int cin, int kf, int kd, void* stream) {
     const int total = cout * cin * 27;

@@ -41,7 +41,6 @@ class _Lib:
                                   C.c_int, C.c_int, C.c_void_p]
         d.coinn_orthogonalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
         d.coinn_gemm_bf16_tn.argtypes = [C.c_void_p] * 4 + [C.c_int] * 10 + [C.c_void_p]
-        d.coinn_conv1_fwd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_bn_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
         d.coinn_bn_finalize.argtypes = [C.c_void_p] * 5 + [C.c_float] * 3 + [C.c_int, C.c_void_p]
         d.coinn_bn_finalize2.argtypes = [C.c_void_p] * 5 + [C.c_float] * 3 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
@@ -50,15 +49,11 @@ class _Lib:
         d.coinn_bn_relu_pool_bwd.argtypes = [C.c_void_p] * 8 + [C.c_int] * 6 + [C.c_void_p]
         d.coinn_conv3d_igemm.argtypes = [C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p]
         d.coinn_conv3d_tma.argtypes = [C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p]
-        d.coinn_conv1_fwd_tc.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_conv1_padded_shape.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
-        d.coinn_conv1_pad_input.argtypes = [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
-        d.coinn_conv1_fwd_toeplitz.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_conv1_pad_input_hd.argtypes = [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_conv1_fused_stats.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_conv1_fused_pool.argtypes = [C.c_void_p] * 8 + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_conv1_fused_bwd.argtypes = [C.c_void_p] * 9 + [C.c_int] * 4 + [C.c_void_p]
-        d.coinn_conv1_wgrad_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_conv3d_halo.argtypes = [C.c_void_p] * 3 + [C.c_int] * 8 + [C.c_void_p]
         d.coinn_conv3d_halo_stats.argtypes = [C.c_void_p] * 4 + [C.c_int] * 8 + [C.c_void_p]
         d.coinn_conv3d_wgrad_halo.argtypes = [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]
@@ -68,7 +63,6 @@ class _Lib:
         d.coinn_pack_conv_weights.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_linear_small_fwd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_linear_small_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p]
-        d.coinn_conv1_wgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
 
     def __getattr__(self, name):
         return getattr(self.dll, name)

@@ -13,7 +13,8 @@ Blocks 2-5 (stored conv output y):
 Block 1 (C_in = 1, 543 MB of y at the benchmark shape) stores nothing at full resolution: the banded-Toeplitz tcgen05
 convolution is recomputed in a statistics pass, a BN+ReLU+pool pass (pooled output + one arg-max code byte per value)
 and the backward pass, where the gradient tile goes from registers to shared memory and straight into the weight-gradient
-MMAs (``conv1_fused_*`` below; COINN_CONV1_FUSED=0 selects the stored-y kernels instead).
+MMAs (``conv1_fused_*`` below).  The stored-y first-block kernels of round 1 (CUDA-core conv1, conv1_tc, stored-y Toeplitz)
+were superseded by this path and removed.
 
 For comparison the PyTorch chain is conv, BN-stat, BN-apply, ReLU, pool - each a full read+write - and its
 channels-last-3d BatchNorm backward alone takes 40 ms per step on a B200 (profiles/r1_launches_torchmodules.txt).
@@ -42,35 +43,6 @@ def _chk(code, what):
 
 
 # ------------------------------------------------------------------------------------ kernels
-def conv1_impl(which='fwd'):
-    """'tc': tcgen05 kernels of conv1_tc.cu; 'cuda': the CUDA-core kernels of vbm_fused.cu.
-    Measured on B200 for the 8 x 121x145x121 batch (scripts/prof_bn.py): forward 613 us (cuda) vs 523 us (tc);
-    wgrad 1124 us (cuda) vs 310 us (tc) -> both default to tc.  COINN_CONV1_IMPL overrides both,
-    COINN_CONV1_FWD / COINN_CONV1_WGRAD one of them.  bf16 volumes (the PCIe-friendly host format) are up-cast
-    to fp32 once on the device: the kernels read fp32 taps faster than 2-byte taps (3.31 vs 3.75 ms per step)."""
-    import os
-    both = os.environ.get('COINN_CONV1_IMPL')
-    if both:
-        return both
-    if which == 'fwd':
-        return os.environ.get('COINN_CONV1_FWD', 'toeplitz')
-    return os.environ.get('COINN_CONV1_WGRAD', 'tc')
-
-
-def conv1_pad_input(x):
-    """[N,D,H,W] fp32/bf16 volume -> zero-padded bf16 row matrix [N*(D+2)*(H+2), Wq] that the banded-Toeplitz
-    tcgen05 kernels (conv1_toeplitz.cu) read by TMA; one pass over the input (replaces the bf16->fp32 up-cast)."""
-    N, D, H, W = x.shape
-    x = x.contiguous() if x.dtype in (BF16, _torch.float32) else x.float().contiguous()
-    rows, cols = _C.c_longlong(0), _C.c_int(0)
-    _nat.lib().coinn_conv1_padded_shape(N, D, H, W, _C.byref(rows), _C.byref(cols))
-    xp = _torch.empty((rows.value, cols.value), dtype=BF16, device=x.device)
-    _chk(_nat.lib().coinn_conv1_pad_input(x.data_ptr(), 1 if x.dtype == BF16 else 0, xp.data_ptr(), N, D, H, W, _sp(x)),
-         'coinn_conv1_pad_input')
-    _bump()
-    return xp
-
-
 _SCRATCH = {}
 
 
@@ -114,9 +86,8 @@ def conv_block_grad_finalize(dwt, acc, conv_w, gamma, beta, cin, cout, transpose
 
 
 def conv1_fused_enabled():
-    """First block without its full-resolution tensors (conv1_fused.cu): conv recomputed in the pool and backward
-    kernels instead of stored.  COINN_CONV1_FUSED=0 falls back to conv1_fwd / bn_relu_pool_* / conv1_wgrad."""
-    return _os.environ.get('COINN_CONV1_FUSED', '1') != '0' and not _os.environ.get('COINN_CONV1_IMPL')
+    """Kept for callers that used to branch on it: the fused first block is the only first-block implementation."""
+    return True
 
 
 def conv1_pad_input_hd(x):
@@ -172,49 +143,6 @@ def conv1_fused_bwd(xp, weight, mean, invstd, gamma, beta, p, code, dp, shape, a
                                           N, D, H, W, _sp(xp)), 'coinn_conv1_fused_bwd')
     _bump(2)
     return dw.view(16, 1, 3, 3, 3), acc[16:], acc[:16]
-
-
-def conv1_fwd(x, weight, impl=None, xp=None):
-    """x: [N,D,H,W] fp32/bf16 (single channel), weight: [16,1,3,3,3] -> (y [N,D,H,W,16] bf16, stats[32])."""
-    N, D, H, W = x.shape
-    impl = impl or conv1_impl('fwd')
-    if impl == 'toeplitz':
-        xp = conv1_pad_input(x) if xp is None else xp
-        w = weight.detach().float().reshape(16, 27).contiguous()
-        y = _torch.empty((N, D, H, W, 16), dtype=BF16, device=x.device)
-        stats = _torch.zeros(32, dtype=_torch.float32, device=x.device)
-        _chk(_nat.lib().coinn_conv1_fwd_toeplitz(xp.data_ptr(), w.data_ptr(), y.data_ptr(), stats.data_ptr(), N, D, H, W, _sp(x)),
-             'coinn_conv1_fwd_toeplitz')
-        _bump()
-        return y, stats
-    keep_bf16 = x.dtype == BF16 and impl == 'tc' and _os.environ.get('COINN_CONV1_BF16_TAPS', '0') == '1'
-    x = x.contiguous() if (keep_bf16 or x.dtype == _torch.float32) else x.float().contiguous()
-    w = weight.detach().float().reshape(16, 27).contiguous()
-    y = _torch.empty((N, D, H, W, 16), dtype=BF16, device=x.device)
-    stats = _torch.zeros(32, dtype=_torch.float32, device=x.device)
-    if impl == 'tc':
-        _chk(_nat.lib().coinn_conv1_fwd_tc(x.data_ptr(), 1 if x.dtype == BF16 else 0, w.data_ptr(), y.data_ptr(),
-                                           stats.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_fwd_tc')
-    else:
-        _chk(_nat.lib().coinn_conv1_fwd(x.data_ptr(), 0, w.data_ptr(), y.data_ptr(),
-                                        stats.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_fwd')
-    _bump()
-    return y, stats
-
-
-def conv1_wgrad(dy, x, impl=None):
-    """dy: [N,D,H,W,16] bf16, x: [N,D,H,W] -> dW [16,1,3,3,3] fp32."""
-    N, D, H, W = x.shape
-    dw = _torch.zeros(16 * 27, dtype=_torch.float32, device=x.device)
-    if (impl or conv1_impl('wgrad')) == 'tc':
-        x = x.contiguous() if x.dtype in (BF16, _torch.float32) else x.float().contiguous()
-        _chk(_nat.lib().coinn_conv1_wgrad_tc(dy.contiguous().data_ptr(), x.data_ptr(), 1 if x.dtype == BF16 else 0,
-                                             dw.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_wgrad_tc')
-    else:
-        _chk(_nat.lib().coinn_conv1_wgrad(dy.data_ptr(), x.data_ptr(), 0 if x.dtype == _torch.float32 else 1,
-                                          dw.data_ptr(), N, D, H, W, _sp(x)), 'coinn_conv1_wgrad')
-    _bump()
-    return dw.view(16, 1, 3, 3, 3)
 
 
 def bn_stats(y, out=None):
@@ -341,7 +269,10 @@ class ConvBnReluPoolFn(_torch.autograd.Function):
                 nbt.add_(1)
             return bn_finalize(stats, count, eps, momentum, running_mean, running_var)
 
-        if first and conv1_fused_enabled():
+        if first:
+            if conv_w.shape[0] != 16 or conv_w.shape[1] != 1:
+                raise ValueError('the fused first block is instantiated for Conv3d(1 -> 16); other first layers go through '
+                                 'the generic blocks (ops.nativize pads C_in)')
             shape = tuple(x.shape)
             xp = conv1_pad_input_hd(x)
             if training:
@@ -353,12 +284,7 @@ class ConvBnReluPoolFn(_torch.autograd.Function):
             ctx.first, ctx.backend, ctx.training, ctx.fused_shape = first, backend, training, shape
             return p
         ctx.fused_shape = None
-        if first:
-            y, stats = conv1_fwd(x, conv_w)
-            if direct:
-                stats_buf.copy_(stats); stats = stats_buf
-        else:
-            y, stats = conv3d_fwd(x, conv_w, backend, want_stats=bool(training), stats_out=stats_buf)
+        y, stats = conv3d_fwd(x, conv_w, backend, want_stats=bool(training), stats_out=stats_buf)
         N, D, H, W, C = y.shape
         if training:
             if stats is None:
@@ -394,14 +320,7 @@ class ConvBnReluPoolFn(_torch.autograd.Function):
             return (None, dw.to(conv_w.dtype), dgamma.to(g.dtype), dbeta.to(b.dtype)) + none
         x, conv_w, y, mean, invstd, g, b, p = ctx.saved_tensors
         dy, dgamma, dbeta = bn_relu_pool_bwd(y, dp.contiguous(), mean, invstd, g, b, p=p, acc=acc)
-        if ctx.first:
-            dx, dw = None, conv1_wgrad(dy, x)
-            if direct:                                    # stored-y first block: dW arrives in the parameter layout
-                dwbuf = _scratch(conv_w_p, 'dw', 27 * cin * cout)
-                dwbuf.copy_(dw.reshape(-1))
-                conv_block_grad_finalize(dwbuf, acc, conv_w_p, gamma_p, beta_p, cin, cout, transposed=False)
-                return (None, None, None, None) + none
-        elif direct:
+        if direct:
             from .conv3d import conv3d_igemm_bwd
             dwbuf = _scratch(conv_w_p, 'dw', 27 * cin * cout)
             dx, _ = conv3d_igemm_bwd(dy, x, conv_w, need_dx=ctx.needs_input_grad[0], raw_dw=dwbuf.view(27 * cin, cout))

@@ -175,36 +175,6 @@ def _ndhwc(t):
     return t.permute(0, 2, 3, 4, 1).contiguous()
 
 
-@pytest.mark.parametrize('impl', ['tc', 'cuda'])
-@pytest.mark.parametrize('shape', [(2, 9, 11, 13), (1, 8, 8, 8), (3, 5, 6, 70), (1, 4, 5, 121), (1, 3, 3, 300)])
-def test_conv1_fwd_and_wgrad(dev, shape, impl, monkeypatch):
-    from coinstac_dinunet_b200.ops import vbm
-    monkeypatch.setenv('COINN_CONV1_IMPL', impl)
-    torch.manual_seed(1)
-    N, D, H, W = shape
-    x = torch.randn(N, D, H, W, device=dev)
-    w = torch.randn(16, 1, 3, 3, 3, device=dev) * 0.2
-    if impl == 'tc':                       # the tensor-core path rounds x and W to bf16: give the oracle the same
-        x, w = x.bfloat16().float(), w.bfloat16().float()
-    y, stats = vbm.conv1_fwd(x, w)
-    ref = torch.nn.functional.conv3d(x.unsqueeze(1), w, padding=1)
-    assert _rel(y, _ndhwc(ref)) < 5e-3
-    yb = y.float().reshape(-1, 16)
-    assert torch.allclose(stats[:16], yb.sum(0), rtol=1e-3, atol=1e-2)
-    assert torch.allclose(stats[16:], (yb * yb).sum(0), rtol=1e-3, atol=1e-2)
-    dy = torch.randn(N, D, H, W, 16, device=dev).to(torch.bfloat16)
-    dw = vbm.conv1_wgrad(dy, x)
-    if impl == 'tc':                       # bf16 volumes can be consumed directly by the tensor-core kernels
-        monkeypatch.setenv('COINN_CONV1_BF16_TAPS', '1')
-        y16, _ = vbm.conv1_fwd(x.bfloat16(), w)
-        assert torch.equal(y16, y)
-        assert torch.allclose(vbm.conv1_wgrad(dy, x.bfloat16()), dw, rtol=1e-4, atol=1e-3)
-    _, dw_ref, _ = torch.ops.aten.convolution_backward(
-        dy.float().permute(0, 4, 1, 2, 3), x.unsqueeze(1), w, None, [1, 1, 1], [1, 1, 1], [1, 1, 1], False,
-        [0, 0, 0], 1, [False, True, False])
-    assert _rel(dw, dw_ref) < 2e-3
-
-
 @pytest.mark.parametrize('C,shape', [(16, (2, 9, 10, 13)), (32, (1, 6, 6, 6)), (128, (2, 4, 7, 5)), (256, (2, 3, 4, 3))])
 def test_bn_relu_pool_block_matches_torch(dev, C, shape):
     """fused stats + BN + ReLU + MaxPool forward and backward vs the PyTorch op chain (fp32)."""
@@ -241,8 +211,9 @@ def test_bn_relu_pool_block_matches_torch(dev, C, shape):
     assert _rel(dy2, _ndhwc(y_ref.grad)) < 2.5e-2
 
 
-def test_native_vbmnet_matches_torch_reference(dev):
-    """whole model: native kernels (conv via the selected backend) vs the plain fp32 PyTorch modules."""
+def test_native_vbmnet_forward_and_buffers_match_fp32_modules(dev):
+    """whole model vs the plain fp32 PyTorch modules: logits and BatchNorm running statistics (the gradient comparison
+    lives in test_hardening_gpu.py, against an oracle that quantises where the kernels do)."""
     from coinstac_dinunet_b200.models import VBMNet
     torch.manual_seed(3)
     shape = (33, 34, 35)
@@ -251,16 +222,8 @@ def test_native_vbmnet_matches_torch_reference(dev):
     nat.load_state_dict(ref.state_dict())
     assert nat.is_native
     x = torch.randn(4, 1, *shape, device=dev)
-    y = torch.randint(0, 2, (4,), device=dev)
     out_ref, out_nat = ref(x), nat(x)
     assert _rel(out_nat, out_ref) < 0.08
-    torch.nn.functional.cross_entropy(out_ref, y).backward()
-    torch.nn.functional.cross_entropy(out_nat, y).backward()
-    for (n1, p1), (_, p2) in zip(ref.named_parameters(), nat.named_parameters()):
-        assert p2.grad is not None and torch.isfinite(p2.grad).all(), n1
-        # bf16 activations flip a few ReLU / arg-max decisions w.r.t. the fp32 oracle: compare direction + scale
-        cos = torch.nn.functional.cosine_similarity(p2.grad.flatten().float(), p1.grad.flatten().float(), dim=0)
-        assert cos > 0.9 and _rel(p2.grad, p1.grad) < 0.45, (n1, float(cos), _rel(p2.grad, p1.grad))
     for (n1, b1), (_, b2) in zip(ref.named_buffers(), nat.named_buffers()):
         assert torch.allclose(b1.float(), b2.float(), rtol=5e-2, atol=5e-3), n1
 
@@ -410,28 +373,6 @@ def test_bucketed_backward_overlap_equals_single_launch(dev):
     assert torch.equal(a1.flat_param, a2.flat_param) and torch.equal(a1.m, a2.m)
     assert int(a1.step_count) == int(a2.step_count) == 5
     assert float(a2.flat_grad.abs().max()) == 0.0
-
-
-@pytest.mark.parametrize('shape', [(2, 9, 11, 13), (1, 5, 140, 30), (2, 3, 4, 121), (1, 20, 9, 64)])
-def test_conv1_toeplitz_fwd(dev, shape):
-    """banded-Toeplitz tcgen05 conv1 (W axis as GEMM K, TMA chunk planes) vs torch conv3d on bf16-rounded operands."""
-    from coinstac_dinunet_b200.ops import vbm
-    torch.manual_seed(3)
-    N, D, H, W = shape
-    x = torch.randn(N, D, H, W, device=dev).bfloat16().float()
-    w = (torch.randn(16, 1, 3, 3, 3, device=dev) * 0.2).bfloat16().float()
-    xp = vbm.conv1_pad_input(x)
-    rows = xp.view(N, D + 2, H + 2, -1)
-    assert torch.equal(rows[:, 1:-1, 1:-1, 1:W + 1].float(), x) and float(rows[:, 0].abs().max()) == 0
-    assert float(rows[..., 0].abs().max()) == 0 and float(rows[..., W + 1:].abs().max()) == 0
-    y, stats = vbm.conv1_fwd(x, w, impl='toeplitz')
-    ref = torch.nn.functional.conv3d(x.unsqueeze(1), w, padding=1)
-    assert _rel(y, _ndhwc(ref)) < 5e-3
-    yb = y.float().reshape(-1, 16)
-    assert torch.allclose(stats[:16], yb.sum(0), rtol=1e-3, atol=1e-2)
-    assert torch.allclose(stats[16:], (yb * yb).sum(0), rtol=1e-3, atol=1e-2)
-    y16, _ = vbm.conv1_fwd(x.bfloat16(), w, impl='toeplitz')          # bf16 volumes: same padded matrix, same result
-    assert torch.equal(y16, y)
 
 
 def _conv1_block_reference(x, w, gamma, beta, dp=None, eps=1e-5):
