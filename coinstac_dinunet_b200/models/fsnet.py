@@ -15,8 +15,9 @@ FS_HIDDEN = (256, 128, 64, 32)
 
 
 class FSNet(_nn.Module):
-    """``native=True``: the Linear layers (forward, dgrad, wgrad) run on the tcgen05 GEMM of
-    ``ops/csrc/gemm_tcgen05.cu`` with the bias fused into the epilogue; parameters / state_dict are unchanged."""
+    """``native=True``: every hidden layer (Linear + BatchNorm1d + ReLU) is ONE fused launch forward and ONE backward
+    (``ops.linear.linear_bn_relu`` -> ``csrc/linear_small.cu`` at site batch sizes; tcgen05 GEMM + BatchNorm for large
+    batches); parameters / buffers / state_dict are unchanged."""
 
     def __init__(self, in_size=FS_INPUT_SIZE, hidden_sizes=FS_HIDDEN, out_size=2, native=False):
         super().__init__()
@@ -35,13 +36,10 @@ class FSNet(_nn.Module):
     def forward(self, x):
         x = x.reshape(x.shape[0], -1)
         if self.native and x.is_cuda:
-            from ..ops.linear import linear as _linear
-            h = x
-            for layer in self.features:
-                if isinstance(layer, _nn.Linear):
-                    h = _linear(h, layer.weight, layer.bias, False).float()
-                else:
-                    h = layer(h)
+            from ..ops.linear import linear as _linear, linear_bn_relu as _lbr
+            h, mods = x, list(self.features)
+            for i in range(0, len(mods), 3):                      # (Linear, BatchNorm1d, ReLU) triples
+                h = _lbr(h, mods[i], mods[i + 1], relu=True)
             return _linear(h, self.classifier.weight, self.classifier.bias, False).float()
         return self.classifier(self.features(x))
 

@@ -26,6 +26,8 @@ def _pooled(shape, n):
 
 
 class ConvBlock(_nn.Module):
+    native_pattern = 'conv_bn_relu_pool'       # ops.nativize: this module IS conv -> bn -> relu -> maxpool(2)
+
     def __init__(self, cin, cout):
         super().__init__()
         self.conv = _nn.Conv3d(cin, cout, kernel_size=3, padding=1, bias=False)

@@ -92,6 +92,10 @@ class NNTrainer:
                 self.nn[name] = self.nn[name].to(memory_format=_torch.channels_last_3d
                                                  if self.cache['channels_last'] == '3d'
                                                  else _torch.channels_last)
+            if self.device['gpu'].type == 'cuda' and self.cache.get('native_ops') \
+                    and not isinstance(self.nn[name], _torch.nn.DataParallel):
+                from ..ops.nativize import nativize      # user-defined modules: matching layer patterns -> sm_100a kernels
+                self.nn[name] = nativize(self.nn[name])
 
     @property
     def compute_dtype(self):

@@ -53,3 +53,4 @@ def _count_launch(n=1):
 
 
 from .api import *  # noqa: E402,F401,F403
+from .nativize import nativize  # noqa: E402,F401

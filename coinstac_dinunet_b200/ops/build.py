@@ -23,7 +23,7 @@ BASE_FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
 FLAGS = BASE_FLAGS + ['--use_fast_math']
 # Optimizer arithmetic is IEEE (sqrt / divide of the Adam update match torch.optim bit for bit up to summation order);
 # fast-math stays on for the conv / GEMM / normalisation kernels whose epilogues tolerate approximate rsqrt / exp.
-EXACT_MATH = {'fused_reduce_opt.cu', 'powersgd.cu', 'rankdad.cu'}
+EXACT_MATH = {'fused_reduce_opt.cu', 'powersgd.cu', 'lowrank.cu'}
 
 
 def flags_for(src):

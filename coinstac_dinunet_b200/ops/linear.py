@@ -182,6 +182,91 @@ class SmallLinearFn(_torch.autograd.Function):
         return dx, dw.to(weight.dtype), (db.to(bias.dtype) if db is not None else None), None
 
 
+class SmallLinearBnReluFn(_torch.autograd.Function):
+    """z = relu?(BatchNorm1d(x @ W^T + b)) for M <= 32 rows in ONE launch each way (``csrc/linear_small.cu``): at these
+    batch sizes the CTA that owns an output feature owns its whole batch column, so the batch statistics, the
+    normalisation, the ReLU and the running-statistics update are the epilogue of the Linear kernel, and BatchNorm's
+    backward is the prologue of the Linear backward.  Replaces Linear + ATen batch_norm + ReLU (3 forward / ~6 backward
+    launches plus dtype casts) in the FreeSurfer MLP (ref model: README.md:31)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, nbt, eps, momentum, training, relu):
+        if x.dtype not in (_torch.float32, _torch.bfloat16):
+            x = x.float()
+        x = x.contiguous()
+        w = weight.detach()
+        w = w if (w.dtype == _torch.float32 and w.is_contiguous()) else w.float().contiguous()
+        b = None if bias is None else bias.detach().float().contiguous()
+        g, be = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        M, K = x.shape
+        N = w.shape[0]
+        z = _torch.empty((M, N), dtype=_torch.float32, device=x.device)
+        xhat = _torch.empty((M, N), dtype=_torch.float32, device=x.device) if training else None
+        invstd = _torch.empty(N, dtype=_torch.float32, device=x.device) if training else None
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        _nat.check(_nat.lib().coinn_linear_bn_small_fwd(
+            x.data_ptr(), 1 if x.dtype == _torch.bfloat16 else 0, w.data_ptr(), ptr(b), g.data_ptr(), be.data_ptr(),
+            ptr(running_mean), ptr(running_var), ptr(nbt) if training else None, ptr(xhat), ptr(invstd), z.data_ptr(),
+            M, N, K, int(relu), int(bool(training)), float(eps), float(momentum), _nat.stream_ptr(x.device)),
+            'coinn_linear_bn_small_fwd')
+        _bump()
+        ctx.save_for_backward(x, w, xhat, invstd, g, be)
+        ctx.params = (weight, bias, gamma, beta)
+        ctx.relu, ctx.training = bool(relu), bool(training)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        if not ctx.training:
+            raise RuntimeError('SmallLinearBnReluFn.backward is only defined for training-mode BatchNorm')
+        x, w, xhat, invstd, g, be = ctx.saved_tensors
+        weight, bias, gamma, beta = ctx.params
+        M, K = x.shape
+        N = w.shape[0]
+        dz = dz.float().contiguous()
+        has_b = bias is not None and ctx.needs_input_grad[2]
+        direct = direct_grad_ok(weight) and w.data_ptr() == weight.data_ptr() and direct_grad_ok(gamma) and \
+            direct_grad_ok(beta) and (not has_b or direct_grad_ok(bias))
+        if direct:
+            dw, db, dg, dbe = weight.grad, (bias.grad if has_b else None), gamma.grad, beta.grad
+        else:
+            dw = _torch.zeros((N, K), dtype=_torch.float32, device=x.device)
+            db = _torch.zeros(N, dtype=_torch.float32, device=x.device) if has_b else None
+            dg, dbe = _torch.zeros(N, dtype=_torch.float32, device=x.device), _torch.zeros(N, dtype=_torch.float32, device=x.device)
+        dx = _torch.zeros((M, K), dtype=_torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        _nat.check(_nat.lib().coinn_linear_bn_small_bwd(
+            dz.data_ptr(), xhat.data_ptr(), invstd.data_ptr(), g.data_ptr(), be.data_ptr(), x.data_ptr(),
+            1 if x.dtype == _torch.bfloat16 else 0, w.data_ptr(), dw.data_ptr(), ptr(db), dg.data_ptr(), dbe.data_ptr(), ptr(dx),
+            M, N, K, int(ctx.relu), _nat.stream_ptr(x.device)), 'coinn_linear_bn_small_bwd')
+        _bump()
+        if dx is not None and x.dtype != _torch.float32:
+            dx = dx.to(x.dtype)
+        tail = (None,) * 7
+        if direct:
+            notify_grad_written(weight, bias if has_b else None, gamma, beta)
+            return (dx, None, None, None, None) + tail
+        return (dx, dw.to(weight.dtype), (db.to(bias.dtype) if db is not None else None), dg.to(gamma.dtype),
+                dbe.to(beta.dtype)) + tail
+
+
+def linear_bn_relu(x, lin, bn, relu=True):
+    """``relu?(bn(lin(x)))`` for an ``nn.Linear`` + ``nn.BatchNorm1d`` pair: fused small-batch kernel when it applies
+    (CUDA, M <= 32, affine BatchNorm with running statistics or training mode), PyTorch composition otherwise."""
+    x2 = x.reshape(-1, x.shape[-1])
+    fused = (x2.is_cuda and x2.shape[0] <= SMALL_M and bn.affine and lin.weight.dtype == _torch.float32
+             and (bn.training or bn.track_running_stats) and (not bn.training or x2.shape[0] > 1))
+    if not fused:
+        y = bn(_torch.nn.functional.linear(x2.to(lin.weight.dtype), lin.weight, lin.bias))
+        return y.relu() if relu else y
+    use_batch = bn.training or not bn.track_running_stats
+    mom = bn.momentum if bn.momentum is not None else 0.1
+    tracked = bn.track_running_stats
+    return SmallLinearBnReluFn.apply(x2, lin.weight, lin.bias, bn.weight, bn.bias,
+                                     bn.running_mean if tracked else None, bn.running_var if tracked else None,
+                                     bn.num_batches_tracked if tracked else None, bn.eps, mom, use_batch, relu)
+
+
 def linear(x, weight, bias, relu):
     """Dispatch: small-batch CUDA-core kernels (M <= 32) or the tcgen05 GEMM path."""
     if x.shape[0] <= SMALL_M:

@@ -27,6 +27,13 @@ class FusedArgs(C.Structure):
     ]
 
 
+class AllGatherArgs(C.Structure):
+    """Mirror of ``coinn::AllGatherArgs`` (csrc/lowrank.cu)."""
+    _fields_ = [('src_ptrs', C.c_void_p * MAX_RANKS), ('flag_ptrs', C.c_void_p * MAX_RANKS), ('dst', C.c_void_p),
+                ('epoch', C.c_void_p), ('error', C.c_void_p), ('numel', C.c_longlong), ('rank', C.c_int), ('world', C.c_int),
+                ('timeout_ms', C.c_uint), ('_pad', C.c_int)]
+
+
 class _Lib:
     def __init__(self):
         self.dll = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
@@ -62,7 +69,26 @@ class _Lib:
         d.coinn_bn_pool_bwd_stats_pooled.argtypes = [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_void_p]
         d.coinn_pack_conv_weights.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_linear_small_fwd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
+        d.coinn_linear_bn_small_fwd.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_int] * 5 + [C.c_float] * 2 + [C.c_void_p]
+        d.coinn_linear_bn_small_bwd.argtypes = [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
         d.coinn_linear_small_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p]
+
+        # MX-FP8 (csrc/mxfp8.cu)
+        d.coinn_quantize_mx.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]
+        d.coinn_gemm_mxfp8_tn.argtypes = [C.c_void_p] * 6 + [C.c_int] * 8 + [C.c_void_p]
+        # low-rank engines (csrc/lowrank.cu)
+        d.coinn_psgd_mq.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        d.coinn_psgd_mtp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        d.coinn_psgd_reconstruct.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        d.coinn_orthogonalize_batched.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
+        d.coinn_segcopy.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        d.coinn_gram_seg.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        d.coinn_lowrank_eig.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        d.coinn_skinny_gemm_seg.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p]
+        d.coinn_dad_reconstruct.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        d.coinn_allgather.argtypes = [C.POINTER(AllGatherArgs), C.c_void_p]
+        if d.coinn_allgather_args_size() != C.sizeof(AllGatherArgs):
+            raise RuntimeError('AllGatherArgs ABI mismatch')
 
     def __getattr__(self, name):
         return getattr(self.dll, name)

@@ -546,6 +546,38 @@ class SymmAllReduce:
             self.error = _torch.zeros(1, dtype=_torch.int32, device=self.device)
             self.dummy = _torch.zeros(4, dtype=_torch.float32, device=self.device)
 
+    def mean_inplace(self, numel):
+        """Zero-copy form: the caller has written ``inp.local[:numel]`` (e.g. a kernel produced the PowerSGD factors
+        right there); afterwards ``out.local[:numel]`` holds the mean over all ranks and ``inp.local`` is zero again.
+        Returns ``out.local``.  Native only (CUDA)."""
+        assert self.native and numel <= self.capacity
+        if self.world == 1:
+            self.out.local[:numel].copy_(self.inp.local[:numel])
+            self.inp.local[:numel].zero_()
+            return self.out.local
+        self._launch_mean(_round_up(int(numel), 4 * self.world))
+        return self.out.local
+
+    def _launch_mean(self, n4):
+        nat = self._nat
+        v = self.variant
+        if v == 'auto':
+            v = 'one_shot' if n4 * 4 <= _conf.ONE_SHOT_MAX_BYTES else ('nvls' if self.inp.multicast_ptr and self.out.multicast_ptr else 'two_shot')
+        a = nat.FusedArgs()
+        for r in range(self.world):
+            a.grad_ptrs[r], a.param_ptrs[r], a.flag_ptrs[r] = self.inp.peer_ptrs[r], self.out.peer_ptrs[r], self.flags.peer_ptrs[r]
+        a.grad_mc = self.inp.multicast_ptr or None
+        a.param_mc = self.out.multicast_ptr or None
+        a.m, a.v = self.dummy.data_ptr(), self.dummy.data_ptr()
+        a.epoch, a.step, a.ticket = self.epoch.data_ptr(), self.step.data_ptr(), self.ticket.data_ptr()
+        a.offset, a.numel = 0, n4
+        a.rank, a.world, a.variant, a.opt_kind, a.grad_dtype = self.rank, self.world, _VARIANTS[v], _OPT_KINDS['none'], 0
+        a.zero_grads, a.bump_step, a.grad_scale = 1, 0, 1.0 / self.world
+        a.error, a.timeout_ms = self.error.data_ptr(), _DEFAULT_TIMEOUT_MS
+        nat.check(nat.lib().coinn_fused_reduce_opt(_C.byref(a), 0, nat.stream_ptr(self.device)), 'fused all-reduce')
+        from .. import ops as _ops
+        _ops._count_launch()
+
     def mean_(self, tensors):
         """Replace every tensor in ``tensors`` by its mean over all ranks (in place)."""
         tensors = [t for t in tensors if t.numel()]
@@ -557,32 +589,61 @@ class SymmAllReduce:
             _dist.all_reduce(flat, group=self.group)
             flat /= self.world
         else:
-            nat = self._nat
-            n4 = _round_up(total, 4 * self.world)
             off = 0
             for t in tensors:
                 self.inp.local[off:off + t.numel()].copy_(t.reshape(-1))
                 off += t.numel()
-            v = self.variant
-            if v == 'auto':
-                v = 'one_shot' if n4 * 4 <= _conf.ONE_SHOT_MAX_BYTES else ('nvls' if self.inp.multicast_ptr and self.out.multicast_ptr else 'two_shot')
-            a = nat.FusedArgs()
-            for r in range(self.world):
-                a.grad_ptrs[r], a.param_ptrs[r], a.flag_ptrs[r] = self.inp.peer_ptrs[r], self.out.peer_ptrs[r], self.flags.peer_ptrs[r]
-            a.grad_mc = self.inp.multicast_ptr or None
-            a.param_mc = self.out.multicast_ptr or None
-            a.m, a.v = self.dummy.data_ptr(), self.dummy.data_ptr()
-            a.epoch, a.step, a.ticket = self.epoch.data_ptr(), self.step.data_ptr(), self.ticket.data_ptr()
-            a.offset, a.numel = 0, n4
-            a.rank, a.world, a.variant, a.opt_kind, a.grad_dtype = self.rank, self.world, _VARIANTS[v], _OPT_KINDS['none'], 0
-            a.zero_grads, a.bump_step, a.grad_scale = 1, 0, 1.0 / self.world
-            a.error, a.timeout_ms = self.error.data_ptr(), _DEFAULT_TIMEOUT_MS
-            nat.check(nat.lib().coinn_fused_reduce_opt(_C.byref(a), 0, nat.stream_ptr(self.device)), 'fused all-reduce')
-            from .. import ops as _ops
-            _ops._count_launch()
+            self._launch_mean(_round_up(total, 4 * self.world))
             flat = self.out.local
         off = 0
         for t in tensors:
             t.copy_(flat[off:off + t.numel()].view_as(t))
             off += t.numel()
         return tensors
+
+
+class SymmAllGather:
+    """All-gather of one flat fp32 buffer per site over symmetric memory (``lowrank.cu::allgather_kernel``): every site
+    writes its payload into its own peer-mapped send buffer, one launch copies all sites' payloads into a local
+    ``[world, numel]`` buffer (16-byte peer loads over NVLink between two flag barriers).  The rankDAD factor exchange
+    (C4 / K12); no NCCL.  ``torch.distributed.all_gather`` off-GPU."""
+
+    def __init__(self, capacity, device, group=None):
+        self.device, self.group = _torch.device(device), group
+        self.world, self.rank = _world(group), _rank(group)
+        self.capacity = _round_up(max(int(capacity), 4), 4)
+        self.native = self.device.type == 'cuda'
+        if self.native and self.world > 1:
+            from ..ops import native as _nat
+            self._nat = _nat
+            self.send = SymmetricBuffer(self.capacity, _torch.float32, self.device, group)
+            self.flags = SymmetricBuffer(_nat.lib().coinn_allgather_flag_slots(), _torch.int32, self.device, group)
+            self.epoch = _torch.zeros(_nat.lib().coinn_allgather_max_blocks(), dtype=_torch.int32, device=self.device)
+            self.error = _torch.zeros(1, dtype=_torch.int32, device=self.device)
+        else:
+            self.send = _Local(self.capacity, _torch.float32, self.device)
+        self.recv = _torch.zeros(max(self.world, 1) * self.capacity, dtype=_torch.float32, device=self.device)
+
+    def gather(self, numel):
+        """``send.local[:numel]`` of every site -> returns ``recv`` viewed as ``[world, stride]`` (row s = site s's
+        payload in ``[:numel]``) and the row stride in elements."""
+        n4 = _round_up(int(numel), 4)
+        assert n4 <= self.capacity
+        if self.world == 1:
+            self.recv[:n4].copy_(self.send.local[:n4])
+            return self.recv[:n4].view(1, n4), n4
+        if not self.native:
+            parts = [_torch.empty(n4, dtype=_torch.float32, device=self.device) for _ in range(self.world)]
+            _dist.all_gather(parts, self.send.local[:n4].contiguous(), group=self.group)
+            self.recv[:self.world * n4].copy_(_torch.cat(parts))
+            return self.recv[:self.world * n4].view(self.world, n4), n4
+        nat = self._nat
+        a = nat.AllGatherArgs()
+        for r in range(self.world):
+            a.src_ptrs[r], a.flag_ptrs[r] = self.send.peer_ptrs[r], self.flags.peer_ptrs[r]
+        a.dst, a.epoch, a.error = self.recv.data_ptr(), self.epoch.data_ptr(), self.error.data_ptr()
+        a.numel, a.rank, a.world, a.timeout_ms = n4, self.rank, self.world, _DEFAULT_TIMEOUT_MS
+        nat.check(nat.lib().coinn_allgather(_C.byref(a), nat.stream_ptr(self.device)), 'coinn_allgather')
+        from .. import ops as _ops
+        _ops._count_launch()
+        return self.recv[:self.world * n4].view(self.world, n4), n4

@@ -263,7 +263,52 @@ class NvlinkPowerSGDLearner(NvlinkLearner):
             red = self.cache['_symm_allreduce'] = SymmAllReduce(max(need, 1 << 16), self.device)
         red.mean_(tensors)
 
+    def _device_path(self):
+        return self.device.type == 'cuda' and self.arena.backend in ('nvlink', 'nccl') \
+            and int(self.rank_r) <= 8 and self.cache.get('lowrank_kernels', True)
+
+    def _compressed_step_device(self):
+        """One compressed step entirely on the hand-written kernels (``ops/lowrank.py`` + the fused all-reduce): no
+        ``torch.distributed`` collective, no ``torch.matmul``.  Ten launches for the whole model:
+
+            orthogonalize(Q) | M = G + E, P = M Q | all-reduce(P) | orthogonalize(P) | Q = M^T P | gather rank-1 grads
+            | all-reduce(Q + rank-1) | scatter rank-1 | G = P Q^T, E = M - G | fused local optimizer step
+
+        The factor buffers ARE the symmetric exchange buffers (kernels write P / Q straight into ``SymmAllReduce.inp`` and
+        read the averaged factors from ``.out``), the warm-start Q is the averaged Q of the previous step, and the error
+        memory is one flat buffer laid out like the gradient arena (ref powersgd/__init__.py:61-181)."""
+        from ..ops.lowrank import PowerSGDPlan
+        from .arena import SymmAllReduce
+        arena, st, c = self.arena, self.st, self.cache
+        plan = c.get('_psgd_plan')
+        if plan is None or plan.rank != int(self.rank_r) or c.get('_psgd_arena') is not arena:
+            plan = c['_psgd_plan'] = PowerSGDPlan(arena.params, arena.offsets, int(self.rank_r), self.device)
+            c['_psgd_arena'] = arena
+            c['_psgd_error'] = _torch.zeros(arena.numel, dtype=_torch.float32, device=self.device)
+            c['_psgd_xp'] = SymmAllReduce(max(plan.p_numel, 4), self.device)
+            c['_psgd_xq'] = SymmAllReduce(max(plan.q_numel + plan.low_numel, 4), self.device)
+            c['_psgd_q_ready'] = False
+        E, xp, xq = c['_psgd_error'], c['_psgd_xp'], c['_psgd_xq']
+        Qavg = xq.out.local                                       # averaged Q of the previous step (warm start)
+        if not (self.warm_start and c['_psgd_q_ready']):
+            gen = _torch.Generator(device='cpu').manual_seed(int(self.seed) + int(st.iter))   # same Q on every site
+            Qavg[:plan.q_numel].copy_(_torch.randn(plan.q_numel, generator=gen).to(self.device))
+            c['_psgd_q_ready'] = True
+        G = arena.flat_grad
+        plan.orthogonalize(Qavg, which=1)
+        plan.mq(G, E, Qavg, xp.inp.local, self.error_feedback)    # E := M = G + E ; P -> exchange buffer
+        Pavg = xp.mean_inplace(plan.p_numel)
+        plan.orthogonalize(Pavg, which=0)
+        plan.mtp(E, Pavg, xq.inp.local)                           # Q = M^T P -> exchange buffer
+        plan.gather_low(G, xq.inp.local)                          # biases / norms ride along uncompressed
+        Qavg = xq.mean_inplace(plan.q_numel + plan.low_numel)
+        plan.scatter_low(Qavg, G)
+        plan.reconstruct(G, E, Pavg, Qavg, self.error_feedback)   # G = P Q^T ; E = M - G
+        arena.local_step()
+
     def _compressed_step(self):
+        if self._device_path():
+            return self._compressed_step_device()
         from ..distrib.powersgd import _native_orthogonalize, _as_matrix
         st = self.st
         mats, low = [], []
@@ -333,7 +378,78 @@ class NvlinkDADLearner(NvlinkLearner):
                                                    dtype=self.dtype)
         super().__init__(**kw)
 
+    def _dad_step_device(self):
+        """rankDAD on the device data plane (C4 / K11 / K12): per layer the local (delta, activation) factors come from
+        the coefficient-space power iteration (``ops.lowrank.lowrank_factor``: two Gram launches, one single-CTA
+        eigen-solver, two skinny GEMMs - no cuSOLVER, no host sync) and are written straight into the symmetric send
+        buffer; ONE all-gather launch (peer loads over NVLink) collects every site's factors of every layer; each layer is
+        re-compressed from the gathered column blocks in place and ``dad_reconstruct`` writes ``delta act^T`` (+ the bias
+        column) directly into the gradient arena.  Dense (non-DAD) parameters go through the fused all-reduce.  Zero
+        ``torch.distributed`` collectives, zero ``torch.matmul`` (ref rankdad/__init__.py:63-98, spi.py:190-250)."""
+        from ..distrib.rankdad.spi import _mm_flatten
+        from ..ops.lowrank import dad_reconstruct, lowrank_factor
+        from .arena import SymmAllGather, SymmAllReduce
+        wrapper, c = self.model, self.cache
+        world = _dist.get_world_size() if _dist_on() else 1
+        rank_r, iters, tol = int(wrapper.rank), int(wrapper.num_pow_iters), float(wrapper.dad_tol)
+        layers = wrapper.dad_layers(reverse=True)
+        # ---- layout of the exchange buffer: per layer [left (out x k) | right (in(+1) x k)], 4-element aligned
+        shapes, total = [], 0
+        for name, m in layers:
+            delta, act = _mm_flatten(wrapper._local_grads[name].float(), wrapper._activations[name].float())
+            rows_c = act.shape[1] + (1 if (wrapper.bias_augment and getattr(m, 'bias', None) is not None) else 0)
+            k = max(1, min(rank_r, delta.shape[1], rows_c, delta.shape[0]))
+            lo, ro = total, total + -(-delta.shape[1] * k // 4) * 4
+            total = ro + -(-rows_c * k // 4) * 4
+            shapes.append((name, m, delta, act, rows_c, k, lo, ro))
+        ag = c.get('_dad_gather')
+        if ag is None or ag.capacity < total:
+            ag = c['_dad_gather'] = SymmAllGather(max(total, 4), self.device)
+        send = ag.send.local
+        for name, m, delta, act, rows_c, k, lo, ro in shapes:
+            if rows_c == act.shape[1] + 1:
+                act = _torch.cat([act, act.new_ones(act.shape[0], 1)], dim=1)
+            lowrank_factor(delta.t().contiguous(), act.t().contiguous(), rank_r, iters, tol,
+                           out_left=send[lo:lo + delta.shape[1] * k].view(delta.shape[1], k),
+                           out_right=send[ro:ro + rows_c * k].view(rows_c, k))
+        recv, stride = ag.gather(total)                            # [world, stride]
+        scale = (1.0 / world) if c.get('dad_mean') else 1.0
+        for name, m, delta, act, rows_c, k, lo, ro in shapes:
+            out_f = delta.shape[1]
+            if world > 1 and world * k > rank_r and c.get('dad_recompress', True) and world * k <= 96:
+                left, right = lowrank_factor(None, None, rank_r, iters, tol,
+                                             b_seg=(recv[0, lo:], out_f, world * k, k, stride),
+                                             c_seg=(recv[0, ro:], rows_c, world * k, k, stride))
+            elif world > 1:                                        # no re-compression: concatenate the column blocks
+                left = _torch.cat([recv[s, lo:lo + out_f * k].view(out_f, k) for s in range(world)], 1)
+                right = _torch.cat([recv[s, ro:ro + rows_c * k].view(rows_c, k) for s in range(world)], 1)
+            else:
+                left, right = recv[0, lo:lo + out_f * k].view(out_f, k), recv[0, ro:ro + rows_c * k].view(rows_c, k)
+            has_bias = getattr(m, 'bias', None) is not None
+            if left.shape[1] <= 16:
+                dad_reconstruct(left, right, m.weight.grad, m.bias.grad if has_bias else None, scale=scale)
+                if has_bias and rows_c == m.weight.shape[1]:       # no bias column carried: the reference's approximation
+                    m.bias.grad.copy_(left.sum(1) * scale)
+            else:                                                  # wide un-recompressed factors: plain product
+                full = (left * scale) @ right.t()
+                m.weight.grad.copy_(full[:, :m.weight.shape[1]])
+                if has_bias:
+                    m.bias.grad.copy_(full[:, -1] if rows_c == m.weight.shape[1] + 1 else left.sum(1) * scale)
+        plain = [p.grad for p in wrapper.plain_parameters() if p.grad is not None]
+        if plain and world > 1:
+            red = c.get('_symm_allreduce')
+            need = sum(t.numel() for t in plain)
+            if red is None or red.capacity < need:
+                red = c['_symm_allreduce'] = SymmAllReduce(max(need, 1 << 16), self.device)
+            red.mean_(plain)
+            if not c.get('dad_mean'):
+                _torch._foreach_mul_(plain, float(world))          # rankDAD exchanges sums (quirk 8.5-9)
+        self.arena.local_step()
+
     def _dad_step(self):
+        if self.device.type == 'cuda' and self.arena.backend in ('nvlink', 'nccl') and self.cache.get('lowrank_kernels', True) \
+                and int(self.model.rank) <= 16:
+            return self._dad_step_device()
         from ..distrib.rankdad.spi import power_iteration_BC
         wrapper = self.model
         world = _dist.get_world_size() if _dist_on() else 1

@@ -26,6 +26,32 @@ def scenario_protocol(work, opts):
                 precision_bits=int(opts.get('precision_bits', 32)),
                 gpus=[int(os.environ.get('LOCAL_RANK', 0))] if torch.cuda.is_available() else None)
     eng = DistEngine(work, inputspec=spec)
+    # count torch.distributed collectives issued INSIDE a compressed / rankDAD optimizer step (the device data plane
+    # must not issue any: the exchange is in-kernel over symmetric memory)
+    import coinstac_dinunet_b200.parallel.nvlink_learner as nvl
+    inside = {'flag': False, 'calls': 0, 'steps': 0}
+    for fn_name in ('all_reduce', 'all_gather', 'broadcast', 'all_gather_into_tensor', 'reduce_scatter_tensor', 'all_to_all_single'):
+        orig = getattr(dist, fn_name, None)
+        if orig is None:
+            continue
+
+        def counted(*a, _orig=orig, **kw):
+            if inside['flag']:
+                inside['calls'] += 1
+            return _orig(*a, **kw)
+        setattr(dist, fn_name, counted)
+        setattr(nvl._dist, fn_name, counted)
+    for cls, meth in ((nvl.NvlinkPowerSGDLearner, '_compressed_step'), (nvl.NvlinkDADLearner, '_dad_step')):
+        orig_m = getattr(cls, meth)
+
+        def wrapped(self, _orig=orig_m):
+            inside['flag'] = True
+            inside['steps'] += 1
+            try:
+                return _orig(self)
+            finally:
+                inside['flag'] = False
+        setattr(cls, meth, wrapped)
     sizes = [24, 18, 30, 12, 20, 16, 28, 22]
     write_synthetic_site(eng.state['baseDirectory'], sizes[eng.rank % len(sizes)], (66,), seed=eng.rank)
     local_kw = {'pretrain_args': {'epochs': 2}} if opts.get('pretrain') == '1' else None
@@ -40,7 +66,8 @@ def scenario_protocol(work, opts):
         res = {'rounds': rounds, 'replicas_identical': bool(same), 'csv': os.path.exists(csv),
                'backend': eng.cache['_arena'].backend, 'fused_steps': eng.cache['_arena'].steps_done,
                'graphed': '_graph_step' in eng.cache, 'param_sum': float(gathered[0].double().sum()),
-               'trace': [t['remote'] for t in eng.trace], 'weights_broadcast': eng.cache.get('_weights_broadcast')}
+               'trace': [t['remote'] for t in eng.trace], 'weights_broadcast': eng.cache.get('_weights_broadcast'),
+               'collectives_in_steps': inside['calls'], 'compressed_steps': inside['steps']}
         with open(os.path.join(work, 'result.json'), 'w') as fp:
             json.dump(res, fp)
 

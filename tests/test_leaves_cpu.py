@@ -259,3 +259,50 @@ def test_native_library_exports_every_declared_symbol():
     assert len(names) >= 25
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
+
+
+def test_nativize_plans_user_models_without_touching_state_dict():
+    """ops.nativize on a user-defined CNN: the plan covers conv stacks (with channel padding) and Linear(+BN1d)(+ReLU)
+    groups, module names / state_dict keys / parameters are untouched and the CPU forward is the original one."""
+    import torch
+    from torch import nn
+    from coinstac_dinunet_b200.ops.nativize import NativeSequential, _padded_pair, nativize
+
+    class UserNet(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.features = nn.Sequential(
+                nn.Conv3d(1, 8, 3, padding=1), nn.BatchNorm3d(8), nn.ReLU(), nn.MaxPool3d(2),
+                nn.Conv3d(8, 24, 3, padding=1, bias=False), nn.BatchNorm3d(24), nn.ReLU(inplace=True), nn.MaxPool3d(2),
+                nn.Conv3d(24, 48, 3, padding=1), nn.BatchNorm3d(48), nn.ReLU(), nn.MaxPool3d(2),
+                nn.Dropout3d(0.0))
+            self.head = nn.Sequential(nn.Flatten(), nn.Linear(48 * 8, 64), nn.BatchNorm1d(64), nn.ReLU(), nn.Linear(64, 32),
+                                      nn.ReLU(), nn.Linear(32, 2))
+
+        def forward(self, x):
+            return self.head(self.features(x))
+
+    torch.manual_seed(0)
+    net = UserNet()
+    keys = list(net.state_dict().keys())
+    params = [id(p) for p in net.parameters()]
+    x = torch.randn(2, 1, 16, 16, 16)
+    net.eval()
+    want = net(x)
+    report = []
+    out = nativize(net, report=report)
+    assert out is net and isinstance(net.features, NativeSequential) and isinstance(net.head, NativeSequential)
+    assert list(net.state_dict().keys()) == keys and [id(p) for p in net.parameters()] == params
+    assert torch.equal(net(x), want)                                   # CPU: original path
+    kinds = [(r[0], r[1]) for r in report]
+    assert ('features', 'conv_stack') in kinds and ('head', 'linear_bn_relu') in kinds
+    assert ('head', 'linear_relu') in kinds and ('head', 'linear') in kinds
+    stack = [r for r in report if r[1] == 'conv_stack'][0][2]
+    assert stack == [(1, 8), (8, 24), (24, 48)]
+    assert _padded_pair(1, 8) == (16, 32) and _padded_pair(24, 48) == (32, 64) and _padded_pair(48, 96) == (64, 128)
+    assert _padded_pair(300, 10) is None
+    plan = net.features._native_plan
+    assert plan[0][0] == 'stack' and plan[-1][0] == 'mod'              # Dropout3d stays a torch module
+    # strides / kernel sizes the kernels do not implement stay on the torch path
+    other = nn.Sequential(nn.Conv3d(4, 8, 5, padding=2), nn.BatchNorm3d(8), nn.ReLU(), nn.MaxPool3d(2))
+    assert not isinstance(nativize(other), NativeSequential)

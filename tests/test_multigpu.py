@@ -33,7 +33,16 @@ def test_symm_allreduce_matches_nccl(tmp_path):
 
 def test_powersgd_protocol_over_nvlink(tmp_path):
     res = run_workers('protocol', tmp_path, nproc=_n(), port=29704, extra=['transport=nvlink', 'agg_engine=powerSGD'])
-    assert res['backend'] == 'nvlink' and res['csv'] and res['trace'][-2] == 'success'
+    assert res['backend'] == 'nvlink' and res['csv'] and res['trace'][-2] == 'success' and res['replicas_identical']
+    # K10: P = MQ, Q = M^T P, P Q^T + error feedback and both factor exchanges run in our kernels
+    assert res['compressed_steps'] > 0 and res['collectives_in_steps'] == 0, res
+
+
+def test_rankdad_protocol_over_nvlink(tmp_path):
+    res = run_workers('protocol', tmp_path, nproc=_n(), port=29711, extra=['transport=nvlink', 'agg_engine=rankDAD'])
+    assert res['backend'] == 'nvlink' and res['csv'] and res['trace'][-2] == 'success' and res['replicas_identical']
+    # K11 / K12: factor all-gather over symmetric memory, coefficient-space power iteration, reconstruct-into-grad
+    assert res['compressed_steps'] > 0 and res['collectives_in_steps'] == 0, res
 
 
 def test_bucketed_overlap_matches_single_launch(tmp_path):

@@ -552,3 +552,217 @@ def test_conv3d_wgrad_tap_matches_torch(dev, cin, cout, shape, monkeypatch):
         dy.float().permute(0, 4, 1, 2, 3), x.float().permute(0, 4, 1, 2, 3), w, None, [1, 1, 1], [1, 1, 1], [1, 1, 1],
         False, [0, 0, 0], 1, [False, True, False])
     assert _rel(dw, dw_ref) < 5e-3, _rel(dw, dw_ref)
+
+
+@pytest.mark.parametrize('M,K,N,relu', [(16, 66, 256, True), (16, 256, 128, True), (8, 64, 32, True), (32, 130, 33, False),
+                                        (2, 9, 5, True)])
+def test_fused_linear_bn1d_relu_matches_torch(dev, M, K, N, relu):
+    """Linear + BatchNorm1d (training) + ReLU in one launch each way vs the PyTorch module chain, incl. running statistics,
+    num_batches_tracked, in-place .grad accumulation and eval mode."""
+    from coinstac_dinunet_b200.ops.linear import linear_bn_relu
+    torch.manual_seed(M + K + N)
+    lin, bn = torch.nn.Linear(K, N).to(dev), torch.nn.BatchNorm1d(N).to(dev)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.weight[::3] *= -1; bn.bias.normal_(0, 0.3)
+    lin_r, bn_r = torch.nn.Linear(K, N).to(dev), torch.nn.BatchNorm1d(N).to(dev)
+    lin_r.load_state_dict(lin.state_dict()); bn_r.load_state_dict(bn.state_dict())
+    x = torch.randn(M, K, device=dev)
+    xr = x.clone().requires_grad_(True)
+    zr = bn_r(lin_r(xr))
+    zr = zr.relu() if relu else zr
+    g = torch.randn_like(zr)
+    zr.backward(g)
+    x1 = x.clone().requires_grad_(True)
+    z = linear_bn_relu(x1, lin, bn, relu=relu)
+    assert torch.allclose(z, zr, rtol=1e-3, atol=1e-4), float((z - zr).abs().max())
+    z.backward(g)
+    assert torch.allclose(bn.running_mean, bn_r.running_mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(bn.running_var, bn_r.running_var, rtol=1e-4, atol=1e-5)
+    assert int(bn.num_batches_tracked) == 1
+    for a, b, name in ((lin.weight.grad, lin_r.weight.grad, 'dW'), (bn.weight.grad, bn_r.weight.grad, 'dgamma'),
+                       (bn.bias.grad, bn_r.bias.grad, 'dbeta'), (x1.grad, xr.grad, 'dx')):
+        assert _rel(a, b) < 2e-3, (name, _rel(a, b))
+    assert float(lin.bias.grad.abs().max()) < 1e-4            # a bias in front of BatchNorm has (numerically) no gradient
+    # direct mode: existing fp32 .grad buffers are accumulated into in place, autograd gets None
+    wp = lin.weight.grad.data_ptr()
+    before = lin.weight.grad.clone()
+    linear_bn_relu(x.clone(), lin, bn, relu=relu).backward(g)
+    assert lin.weight.grad.data_ptr() == wp and _rel(lin.weight.grad - before, lin_r.weight.grad) < 5e-3
+    # eval mode uses the running statistics
+    bn.eval(); bn_r.eval()
+    with torch.no_grad():
+        ze = linear_bn_relu(x, lin, bn, relu=relu)
+        zer = bn_r(lin_r(x)); zer = zer.relu() if relu else zer
+    assert torch.allclose(ze, zer, rtol=2e-3, atol=2e-4)
+
+
+def test_native_fsnet_matches_reference_modules(dev):
+    """FreeSurfer MLP on the fused Linear+BN1d+ReLU kernels vs the stock modules: logits, every gradient, BN buffers."""
+    from coinstac_dinunet_b200.models import FSNet
+    torch.manual_seed(2)
+    ref, nat = FSNet().to(dev), FSNet(native=True).to(dev)
+    nat.load_state_dict(ref.state_dict())
+    ref.train(); nat.train()
+    x = torch.randn(16, 66, device=dev)
+    y = torch.randint(0, 2, (16,), device=dev)
+    o_ref, o_nat = ref(x), nat(x)
+    assert torch.allclose(o_nat, o_ref, rtol=2e-3, atol=2e-4)
+    torch.nn.functional.cross_entropy(o_ref, y).backward()
+    torch.nn.functional.cross_entropy(o_nat, y).backward()
+    for (n1, p1), (_, p2) in zip(ref.named_parameters(), nat.named_parameters()):
+        if n1.endswith('bias') and n1.startswith('features') and p1.dim() == 1 and 'features.' in n1 and int(n1.split('.')[1]) % 3 == 0:
+            assert float(p2.grad.abs().max()) < 1e-4            # Linear bias under BatchNorm
+            continue
+        assert _rel(p2.grad, p1.grad) < 5e-3, (n1, _rel(p2.grad, p1.grad))
+    for (n1, b1), (_, b2) in zip(ref.named_buffers(), nat.named_buffers()):
+        assert torch.allclose(b1.float(), b2.float(), rtol=1e-4, atol=1e-5), n1
+
+
+# ------------------------------------------------------------------------------------ low-rank engines (K10-K12)
+@pytest.mark.parametrize('rank', [1, 2, 4])
+def test_powersgd_kernels_match_reference_round(dev, rank):
+    """psgd_mq / orthogonalize_batched / psgd_mtp / psgd_reconstruct over several matrices in one launch each, two
+    consecutive rounds (error feedback + warm start carried), vs the PyTorch formulation of the reference's math."""
+    from coinstac_dinunet_b200.ops.lowrank import PowerSGDPlan, powersgd_round_reference
+    torch.manual_seed(rank)
+    shapes = [(256, 66), (128, 256), (300, 1000), (2, 32), (64, 27 * 16), (17,), (256,)]
+    params = [torch.nn.Parameter(torch.randn(*s, device=dev)) for s in shapes]
+    offsets, off = [], 0
+    for p in params:
+        offsets.append(off); off += (p.numel() + 7) // 8 * 8
+    plan = PowerSGDPlan(params, offsets, rank, dev)
+    G = torch.zeros(off, device=dev); E = torch.zeros(off, device=dev)
+    P = torch.zeros(max(plan.p_numel, 4), device=dev); Q = torch.zeros(plan.q_numel + plan.low_numel + 8, device=dev)
+    Qin = torch.randn(plan.q_numel, device=dev)
+    mats = [(i, n, m, g, po, qo) for (i, n, m, g, po, qo) in plan.mats]
+    errs = [torch.zeros(n, m, device=dev) for _, n, m, *_ in mats]
+    qs = [Qin[qo:qo + m * rank].view(m, rank).clone() for _, n, m, g, po, qo in mats]
+    Qcur = Qin.clone()
+    for rnd in range(2):
+        grads = [torch.randn(n, m, device=dev) for _, n, m, *_ in mats]
+        G.zero_()
+        for (_, n, m, g, *_), t in zip(mats, grads):
+            G[g:g + n * m] = t.reshape(-1)
+        low_vals = []
+        for (i, g_off, numel) in plan.low:
+            v = torch.randn(numel, device=dev); G[g_off:g_off + numel] = v; low_vals.append(v)
+        approx, errs, qs = powersgd_round_reference(grads, errs, [q.clone() for q in qs], rank, lambda ts: None)
+        Qbuf = torch.zeros_like(Q); Qbuf[:plan.q_numel] = Qcur
+        plan.orthogonalize(Qbuf, which=1)
+        plan.mq(G, E, Qbuf, P, True)
+        plan.orthogonalize(P, which=0)
+        plan.mtp(E, P, Q)
+        plan.gather_low(G, Q)
+        for (i, g_off, numel), v in zip(plan.low, low_vals):
+            pass
+        plan.scatter_low(Q, G)
+        plan.reconstruct(G, E, P, Q, True)
+        for (_, n, m, g, po, qo), a, e, q in zip(mats, approx, errs, qs):
+            assert _rel(G[g:g + n * m].view(n, m), a) < 2e-4, (rnd, n, m)
+            assert _rel(E[g:g + n * m].view(n, m), e) < 2e-4 + 1e-6
+            assert _rel(Q[qo:qo + m * rank].view(m, rank), q) < 2e-4
+        for (i, g_off, numel), v in zip(plan.low, low_vals):          # rank-1 gradients round-trip unchanged
+            assert torch.equal(G[g_off:g_off + numel], v)
+        Qcur = Q[:plan.q_numel].clone()
+
+
+@pytest.mark.parametrize('rows_b,rows_c,n,rank', [(256, 67, 16, 10), (32, 33, 8, 10), (128, 257, 80, 10), (2, 33, 16, 10),
+                                                   (64, 9217, 32, 4)])
+def test_lowrank_factor_is_the_truncated_svd(dev, rows_b, rows_c, n, rank):
+    """gram -> coefficient-space power iteration -> skinny GEMMs: left @ right.T is the best rank-k approximation of
+    B @ C.T (compared with torch.linalg.svd), and the column-block segmented form gives the same answer."""
+    from coinstac_dinunet_b200.ops.lowrank import lowrank_factor
+    torch.manual_seed(n + rank)
+    decay = torch.logspace(0, -3, n, device=dev)                     # a spectrum with a clear ordering
+    B, C = torch.randn(rows_b, n, device=dev) * decay, torch.randn(rows_c, n, device=dev)
+    left, right = lowrank_factor(B, C, rank, 40, 1e-6)
+    k = left.shape[1]
+    assert k == min(rank, rows_b, rows_c, n) and right.shape == (rows_c, k)
+    full = B.double() @ C.double().t()
+    U, S, Vh = torch.linalg.svd(full, full_matrices=False)
+    best = (U[:, :k] * S[:k]) @ Vh[:k]
+    got = left.double() @ right.double().t()
+    opt_err = float((full - best).norm())
+    assert float((full - got).norm()) <= opt_err * 1.02 + 1e-4 * float(full.norm())
+    # right factors are orthonormal where kept
+    gram = right.t() @ right
+    keep = gram.diagonal() > 0.5
+    assert torch.allclose(gram[keep][:, keep], torch.eye(int(keep.sum()), device=dev), atol=2e-3)
+    if n % 4 == 0 and n >= 8:                                        # segmented operands: 4 column blocks, strided
+        kseg = n // 4
+        stride = (max(rows_b, rows_c) * kseg + 64)
+        bufB, bufC = torch.zeros(4 * stride, device=dev), torch.zeros(4 * stride, device=dev)
+        for s in range(4):
+            bufB[s * stride:s * stride + rows_b * kseg] = B[:, s * kseg:(s + 1) * kseg].reshape(-1)
+            bufC[s * stride:s * stride + rows_c * kseg] = C[:, s * kseg:(s + 1) * kseg].reshape(-1)
+        l2, r2 = lowrank_factor(None, None, rank, 40, 1e-6, b_seg=(bufB, rows_b, n, kseg, stride), c_seg=(bufC, rows_c, n, kseg, stride))
+        assert torch.allclose(l2 @ r2.t(), left @ right.t(), rtol=1e-3, atol=1e-3 * float(full.abs().max()))
+
+
+@pytest.mark.parametrize('out_f,in_f,k,bias', [(256, 66, 10, True), (2, 32, 2, True), (64, 128, 16, False), (33, 9216, 10, True)])
+def test_dad_reconstruct_matches_matmul(dev, out_f, in_f, k, bias):
+    from coinstac_dinunet_b200.ops.lowrank import dad_reconstruct
+    torch.manual_seed(k)
+    delta = torch.randn(out_f, k, device=dev)
+    act = torch.randn(in_f + int(bias), k, device=dev)
+    wg, bg = torch.full((out_f, in_f), 7.0, device=dev), torch.full((out_f,), 7.0, device=dev)
+    dad_reconstruct(delta, act, wg, bg if bias else None, scale=0.5)
+    full = 0.5 * delta @ act.t()
+    assert torch.allclose(wg, full[:, :in_f], rtol=1e-4, atol=1e-4)
+    if bias:
+        assert torch.allclose(bg, full[:, -1], rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------- MX-FP8 (config 4)
+@pytest.mark.parametrize('R,K,dt', [(5, 32, torch.float32), (128, 256, torch.bfloat16), (33, 100, torch.float32), (256, 9216, torch.bfloat16)])
+def test_quantize_mx_matches_reference_and_roundtrips(dev, R, K, dt):
+    from coinstac_dinunet_b200.ops.fp8 import dequantize_mx, quantize_mx, quantize_mx_reference
+    torch.manual_seed(R + K)
+    x = (torch.randn(R, K, device=dev) * torch.logspace(-3, 3, K, device=dev)).to(dt)
+    x[0, :min(K, 32)] = 0                                       # an all-zero block
+    q, sf = quantize_mx(x)
+    q_ref, sf_ref = quantize_mx_reference(x)
+    assert torch.equal(sf, sf_ref)
+    assert torch.equal(q, q_ref)
+    back = dequantize_mx(q, sf, K)
+    xf = x.float()
+    blocks = torch.nn.functional.pad(xf, (0, q.shape[1] - K)).view(R, -1, 32)
+    tol = blocks.abs().amax(-1, keepdim=True) * 2 ** -3         # e4m3: 3 mantissa bits, relative to the block max
+    assert bool(((torch.nn.functional.pad(back, (0, q.shape[1] - K)).view(R, -1, 32) - blocks).abs() <= tol + 1e-30).all())
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 128), (256, 384, 512), (100, 70, 256), (8, 256, 9216), (300, 200, 1152)])
+def test_mxfp8_block_scaled_gemm_matches_dequantised_oracle(dev, M, N, K):
+    """tcgen05.mma.kind::mxf8f6f4.block_scale with scale factors in TMEM vs fp32 matmul of the dequantised operands
+    (exact up to fp32 accumulation order: the products of e4m3 values and power-of-two scales are exact in fp32)."""
+    from coinstac_dinunet_b200.ops.fp8 import dequantize_mx, gemm_mxfp8, quantize_mx
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev) * torch.logspace(-2, 2, K, device=dev)      # scales differ from block to block
+    b = torch.randn(N, K, device=dev) * torch.logspace(1, -1, K, device=dev)
+    aq, asf = quantize_mx(a)
+    bq, bsf = quantize_mx(b)
+    ref = dequantize_mx(aq, asf).double() @ dequantize_mx(bq, bsf).double().t()
+    got = gemm_mxfp8(aq, asf, bq, bsf, split_k=1)
+    assert _rel(got, ref.float()) < 1e-5, _rel(got, ref.float())
+    got2 = gemm_mxfp8(aq, asf, bq, bsf)                           # auto split-K
+    assert _rel(got2, ref.float()) < 1e-5
+    bias = torch.randn(N, device=dev)
+    got3 = gemm_mxfp8(aq, asf, bq, bsf, bias=bias, relu=True, split_k=1, out_dtype=torch.bfloat16)
+    assert _rel(got3, (ref.float() + bias).relu()) < 1e-2
+    # and against the unquantised product: fp8 tolerance
+    assert _rel(got, a @ b.t()) < 6e-2
+
+
+def test_fp8_linear_autograd(dev):
+    from coinstac_dinunet_b200.ops.fp8 import linear_fp8
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(384, 200).to(dev)
+    x = torch.randn(160, 384, device=dev, requires_grad=True)
+    xr = x.detach().clone().requires_grad_(True)
+    y = linear_fp8(x, lin.weight, lin.bias, relu=True)
+    yr = torch.nn.functional.linear(xr, lin.weight, lin.bias).relu()
+    assert _rel(y, yr) < 6e-2
+    g = torch.randn_like(yr)
+    gw_r, gb_r, gx_r = torch.autograd.grad(yr, [lin.weight, lin.bias, xr], g)
+    gw, gb, gx = torch.autograd.grad(y, [lin.weight, lin.bias, x], g)
+    assert _rel(gw, gw_r) < 8e-2 and _rel(gx, gx_r) < 8e-2 and _rel(gb, gb_r) < 5e-2
