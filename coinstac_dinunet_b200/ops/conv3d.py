@@ -80,6 +80,40 @@ def pack_weights(weight):
     return bufs[0], kf, bufs[1], kd
 
 
+FP8_PAIRS = {(32, 64), (64, 128), (128, 256), (64, 32), (128, 64), (256, 128), (32, 32), (64, 64), (128, 128)}
+
+
+def _quantize_rows(x2d, K, box):
+    """x2d: [R, >= K] (row stride = x2d.stride(0)), box = channel-box width in elements (32 / 64 / 128)."""
+    assert x2d.stride(1) == 1 and K % box == 0 and box in (32, 64, 128)
+    if x2d.dtype not in (BF16, _torch.float32):
+        x2d = x2d.float()
+    R, G = x2d.shape[0], box // 32
+    q = _torch.empty((R, K), dtype=_torch.uint8, device=x2d.device)
+    sf = _torch.full((R, K // box), 0x7f7f7f7f, dtype=_torch.int32, device=x2d.device)
+    _nat.check(_nat.lib().coinn_quantize_mx_grouped(x2d.data_ptr(), 1 if x2d.dtype == BF16 else 0, x2d.stride(0), q.data_ptr(),
+                                                    sf.data_ptr(), R, K, G, _nat.stream_ptr(x2d.device)), 'quantize_mx_grouped')
+    _bump(2)
+    return q, sf
+
+
+def _igemm_fp8(x, wk, cin, cout):
+    """MX-FP8 implicit-GEMM conv (``csrc/conv3d_mxfp8.cu``): x [N,D,H,W,cin] bf16, wk [cout, >= 27*cin] bf16 packed
+    (k = tap * cin + ci).  Activations and weights are quantised per 32 input channels (ue8m0 scales) right here."""
+    global last_impl
+    N, D, H, W, _ = x.shape
+    box = min(cin, 128)
+    xq, xsf = _quantize_rows(x.reshape(-1, cin), cin, box)
+    wq, wsf = _quantize_rows(wk, 27 * cin, box)
+    y = _torch.empty((N, D, H, W, cout), dtype=BF16, device=x.device)
+    code = _nat.lib().coinn_conv3d_mxfp8(xq.data_ptr(), xsf.data_ptr(), wq.data_ptr(), wsf.data_ptr(), y.data_ptr(),
+                                         N, D, H, W, cin, cout, _nat.stream_ptr(x.device))
+    _nat.check(code, f'conv3d_mxfp8({cin}->{cout})')
+    last_impl = 'mxfp8'
+    _bump()
+    return y
+
+
 def _igemm(x, wk, kpad, cout, impl=None, stats=None):
     """``stats``: optional zeroed fp32 [2*cout]; filled with the BatchNorm sums of y by the halo kernel's epilogue
     (returns False in ``stats_done`` when the kernel that ran cannot do it)."""
@@ -106,12 +140,16 @@ def _igemm(x, wk, kpad, cout, impl=None, stats=None):
     return y
 
 
-def conv3d_igemm_fwd(x, weight, want_stats=False, stats_out=None):
-    """x: [N,D,H,W,Cin] bf16 contiguous; weight: [Cout,Cin,3,3,3] -> [N,D,H,W,Cout] bf16."""
+def conv3d_igemm_fwd(x, weight, want_stats=False, stats_out=None, fp8=False):
+    """x: [N,D,H,W,Cin] bf16 contiguous; weight: [Cout,Cin,3,3,3] -> [N,D,H,W,Cout] bf16.
+    ``fp8``: MX-FP8 block-scaled kernel where it is instantiated (C_in >= 32), bf16 otherwise."""
     cout, cin = weight.shape[:2]
     if not supported(cin, cout):
         raise ImportError(f'no tcgen05 conv instantiation for {cin}->{cout}')
     wk, kpad, _, _ = pack_weights(weight)
+    if fp8 and (cin, cout) in FP8_PAIRS:
+        y = _igemm_fp8(x.contiguous(), wk, cin, cout)
+        return (y, None) if want_stats else y
     if not want_stats:
         return _igemm(x.contiguous(), wk, kpad, cout)
     stats = stats_out if stats_out is not None else _torch.zeros(2 * cout, dtype=_torch.float32, device=x.device)
@@ -119,7 +157,7 @@ def conv3d_igemm_fwd(x, weight, want_stats=False, stats_out=None):
     return y, (stats if stats_done else None)
 
 
-def conv3d_igemm_bwd(dy, x, weight, need_dx=True, raw_dw=None):
+def conv3d_igemm_bwd(dy, x, weight, need_dx=True, raw_dw=None, fp8=False):
     cout, cin = weight.shape[:2]
     if not supported(cout, cin):
         raise ImportError(f'no tcgen05 conv instantiation for dgrad {cout}->{cin}')
@@ -130,7 +168,10 @@ def conv3d_igemm_bwd(dy, x, weight, need_dx=True, raw_dw=None):
             wd, kpad = _pack_buffers[key][1], (27 * cout + 63) // 64 * 64
         else:
             _, _, wd, kpad = pack_weights(weight)
-        dx = _igemm(dy.contiguous(), wd, kpad, cin)
+        if fp8 and (cout, cin) in FP8_PAIRS:          # dgrad = conv of dy (C = cout) with the flipped / transposed weights
+            dx = _igemm_fp8(dy.contiguous(), wd, cout, cin)
+        else:
+            dx = _igemm(dy.contiguous(), wd, kpad, cin)
     try:
         from .conv3d_wgrad import conv3d_wgrad
         dw = conv3d_wgrad(dy, x, raw_out=raw_dw)

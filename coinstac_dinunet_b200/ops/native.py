@@ -76,6 +76,8 @@ class _Lib:
         # MX-FP8 (csrc/mxfp8.cu)
         d.coinn_quantize_mx.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]
         d.coinn_gemm_mxfp8_tn.argtypes = [C.c_void_p] * 6 + [C.c_int] * 8 + [C.c_void_p]
+        d.coinn_quantize_mx_grouped.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]
+        d.coinn_conv3d_mxfp8.argtypes = [C.c_void_p] * 5 + [C.c_int] * 6 + [C.c_void_p]
         # low-rank engines (csrc/lowrank.cu)
         d.coinn_psgd_mq.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         d.coinn_psgd_mtp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]

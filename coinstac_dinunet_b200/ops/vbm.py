@@ -204,18 +204,18 @@ def conv3d_fwd(x, weight, backend='auto', want_stats=False, stats_out=None):
     """x: [N,D,H,W,Cin] bf16, weight: [Cout,Cin,3,3,3] (any float dtype) -> y [N,D,H,W,Cout] bf16.
     ``want_stats``: -> (y, stats or None); stats = BatchNorm sums produced by the conv epilogue when the kernel can."""
     if want_stats:
-        if backend in ('auto', 'tcgen05'):
+        if backend in ('auto', 'tcgen05', 'fp8'):
             try:
                 from .conv3d import conv3d_igemm_fwd
-                return conv3d_igemm_fwd(x, weight, want_stats=True, stats_out=stats_out)
+                return conv3d_igemm_fwd(x, weight, want_stats=True, stats_out=stats_out, fp8=(backend == 'fp8'))
             except ImportError:
                 if backend == 'tcgen05':
                     raise
         return conv3d_fwd(x, weight, backend), None
-    if backend in ('auto', 'tcgen05'):
+    if backend in ('auto', 'tcgen05', 'fp8'):
         try:
             from .conv3d import conv3d_igemm_fwd
-            return conv3d_igemm_fwd(x, weight)
+            return conv3d_igemm_fwd(x, weight, fp8=(backend == 'fp8'))
         except ImportError:
             if backend == 'tcgen05':
                 raise
@@ -226,10 +226,10 @@ def conv3d_fwd(x, weight, backend='auto', want_stats=False, stats_out=None):
 
 def conv3d_bwd(dy, x, weight, need_dx=True, backend='auto'):
     """-> (dx [N,D,H,W,Cin] bf16 or None, dW [Cout,Cin,3,3,3] fp32)"""
-    if backend in ('auto', 'tcgen05'):
+    if backend in ('auto', 'tcgen05', 'fp8'):
         try:
             from .conv3d import conv3d_igemm_bwd
-            return conv3d_igemm_bwd(dy, x, weight, need_dx)
+            return conv3d_igemm_bwd(dy, x, weight, need_dx, fp8=(backend == 'fp8'))
         except ImportError:
             if backend == 'tcgen05':
                 raise
@@ -258,7 +258,7 @@ class ConvBnReluPoolFn(_torch.autograd.Function):
         g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
         cout = conv_w.shape[0]
         direct = bool(training) and x.is_cuda and _direct_ok(conv_w, gamma, beta) and \
-            (backend in ('auto', 'tcgen05') or first)
+            (backend in ('auto', 'tcgen05', 'fp8') or first)
         ctx.direct, ctx.params = direct, (conv_w, gamma, beta)
         stats_buf = _scratch(conv_w, 'stats', 2 * cout) if direct else None
 
@@ -323,7 +323,8 @@ class ConvBnReluPoolFn(_torch.autograd.Function):
         if direct:
             from .conv3d import conv3d_igemm_bwd
             dwbuf = _scratch(conv_w_p, 'dw', 27 * cin * cout)
-            dx, _ = conv3d_igemm_bwd(dy, x, conv_w, need_dx=ctx.needs_input_grad[0], raw_dw=dwbuf.view(27 * cin, cout))
+            dx, _ = conv3d_igemm_bwd(dy, x, conv_w, need_dx=ctx.needs_input_grad[0], raw_dw=dwbuf.view(27 * cin, cout),
+                                     fp8=(ctx.backend == 'fp8'))
             conv_block_grad_finalize(dwbuf, acc, conv_w_p, gamma_p, beta_p, cin, cout, transposed=True)
             return (dx, None, None, None) + none
         else:

@@ -766,3 +766,55 @@ def test_fp8_linear_autograd(dev):
     gw_r, gb_r, gx_r = torch.autograd.grad(yr, [lin.weight, lin.bias, xr], g)
     gw, gb, gx = torch.autograd.grad(y, [lin.weight, lin.bias, x], g)
     assert _rel(gw, gw_r) < 8e-2 and _rel(gx, gx_r) < 8e-2 and _rel(gb, gb_r) < 5e-2
+
+
+def _dequant_grouped(q, sf, box):
+    R, K = q.shape
+    G = box // 32
+    e = sf.view(torch.uint8).view(R, K // box, 4)[:, :, :G].reshape(R, K // 32).float()
+    return (q.view(torch.float8_e4m3fn).float().view(R, K // 32, 32) * torch.exp2(e - 127).unsqueeze(-1)).view(R, K)
+
+
+@pytest.mark.parametrize('cin,cout,shape', [(32, 64, (2, 6, 7, 9)), (64, 128, (1, 5, 6, 20)), (128, 256, (2, 3, 4, 5)),
+                                            (256, 128, (1, 3, 4, 3)), (64, 32, (1, 4, 9, 7)), (32, 64, (2, 30, 36, 30))])
+def test_mxfp8_conv3d_matches_dequantised_oracle(dev, cin, cout, shape):
+    """Block-scaled fp8 implicit-GEMM conv (per-tap TMA boxes, scale factors gathered at the shifted voxels and staged in
+    TMEM) vs torch conv3d on the dequantised operands: only fp32 accumulation order and the bf16 output rounding differ."""
+    from coinstac_dinunet_b200.ops import conv3d as c3
+    torch.manual_seed(cin + cout)
+    N, D, H, W = shape
+    x = (torch.randn(N, D, H, W, cin, device=dev) * torch.logspace(-1, 1, cin, device=dev)).bfloat16()
+    w = torch.randn(cout, cin, 3, 3, 3, device=dev) * (27 * cin) ** -0.5
+    y = c3.conv3d_igemm_fwd(x, w, fp8=True)
+    assert c3.last_impl == 'mxfp8'
+    box = min(cin, 128)
+    xq, xsf = c3._quantize_rows(x.reshape(-1, cin), cin, box)
+    wk = w.permute(0, 2, 3, 4, 1).reshape(cout, 27 * cin).bfloat16()
+    wq, wsf = c3._quantize_rows(wk, 27 * cin, box)
+    xd = _dequant_grouped(xq, xsf, box).view(N, D, H, W, cin).permute(0, 4, 1, 2, 3)
+    wd = _dequant_grouped(wq, wsf, box).view(cout, 3, 3, 3, cin).permute(0, 4, 1, 2, 3)
+    ref = torch.nn.functional.conv3d(xd.double(), wd.double(), padding=1).float()
+    assert _rel(y, _ndhwc(ref)) < 6e-3, _rel(y, _ndhwc(ref))
+    # against the unquantised conv: fp8 tolerance
+    ref_hp = torch.nn.functional.conv3d(x.float().permute(0, 4, 1, 2, 3), w.bfloat16().float(), padding=1)
+    assert _rel(y, _ndhwc(ref_hp)) < 6e-2
+
+
+def test_fp8_conv_block_trains_like_bf16(dev):
+    """config 4 numerics: a 32->64 block with fp8 fprop/dgrad (bf16 wgrad, fp32 master weights) follows the bf16 block."""
+    from coinstac_dinunet_b200.ops import vbm
+    torch.manual_seed(12)
+    x = torch.randn(2, 8, 10, 12, 32, device=dev).bfloat16()
+    w0 = torch.randn(64, 32, 3, 3, 3, device=dev) * 0.05
+    g0, b0 = torch.rand(64, device=dev) + 0.5, torch.randn(64, device=dev) * 0.1
+    outs = {}
+    for backend in ('auto', 'fp8'):
+        w, g, b = (t.clone().requires_grad_(True) for t in (w0, g0, b0))
+        rm, rv = torch.zeros(64, device=dev), torch.ones(64, device=dev)
+        xin = x.clone().requires_grad_(True)
+        p = vbm.ConvBnReluPoolFn.apply(xin, w, g, b, rm, rv, 1e-5, 0.1, True, backend)
+        dp = torch.ones_like(p) * 0.01 + (torch.arange(p.numel(), device=dev).view_as(p) % 7).to(p.dtype) * 0.01
+        p.backward(dp)
+        outs[backend] = (p.float(), w.grad.clone(), g.grad.clone(), xin.grad.float())
+    for a, b_, name in zip(outs['fp8'], outs['auto'], ('p', 'dw', 'dgamma', 'dx')):
+        assert _rel(a, b_) < 0.12, (name, _rel(a, b_))
