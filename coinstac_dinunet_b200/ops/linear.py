@@ -99,11 +99,12 @@ DIRECT_GRAD_DISABLED = False      # debugging switch: force every gradient throu
 # registers a listener here and the direct-mode kernels call ``notify_grad_written`` right after their launch.
 import weakref as _weakref
 
-_GRAD_LISTENERS = _weakref.WeakKeyDictionary()
+_GRAD_LISTENERS = {}      # id(param) -> (weakref(param), callable); tensors cannot key a Weak*Dictionary (== is elementwise)
 
 
 def register_grad_listener(param, fn):
-    _GRAD_LISTENERS[param] = fn
+    key = id(param)
+    _GRAD_LISTENERS[key] = (_weakref.ref(param, lambda _r, k=key: _GRAD_LISTENERS.pop(k, None)), fn)
 
 
 def notify_grad_written(*params):
@@ -112,9 +113,9 @@ def notify_grad_written(*params):
     for q in params:
         if q is None:
             continue
-        fn = _GRAD_LISTENERS.get(q)
-        if fn is not None:
-            fn()
+        hit = _GRAD_LISTENERS.get(id(q))
+        if hit is not None and hit[0]() is q:
+            hit[1]()
 
 
 def direct_grad_ok(param):

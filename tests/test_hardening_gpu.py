@@ -293,3 +293,56 @@ def test_nativize_user_cnn_trains(dev):
         arena.reduce_and_step()
         losses.append(float(loss))
     assert sum(losses[-5:]) / 5 < 0.25 < sum(losses[:3]) / 3, (losses[:3], losses[-5:])
+
+
+def test_bucketed_overlap_with_direct_grad_kernels(dev):
+    """The native blocks write gradients straight into the arena and hand autograd None, so bucket launches are driven by
+    ops.linear.notify_grad_written instead of autograd hooks: same parameters as the single launch, also inside a
+    whole-step CUDA graph capture (the side stream becomes a branch of the graph)."""
+    from coinstac_dinunet_b200 import ops
+    from coinstac_dinunet_b200.models import VBMNet
+    from coinstac_dinunet_b200.parallel.arena import DistArena
+    shape = (33, 34, 35)
+
+    def make(overlap):
+        torch.manual_seed(0)
+        m = VBMNet(input_shape=shape, native=True).to(dev)
+        a = DistArena(m, torch.optim.Adam(m.parameters(), lr=1e-3), device=dev, backend='nvlink')
+        if overlap:
+            a.enable_overlap(bucket_bytes=1 << 20)
+            assert len(a._overlap['buckets']) >= 2
+        m.train()
+        return m, a
+
+    (m1, a1), (m2, a2) = make(False), make(True)
+    g = torch.Generator(device='cpu').manual_seed(5)
+    for step in range(3):
+        y = torch.randint(0, 2, (4,), generator=g).to(dev)
+        x = torch.randn(4, 1, *shape, generator=g).to(dev)
+        for m, a in ((m1, a1), (m2, a2)):
+            loss, _ = ops.softmax_nll(m(x), y)
+            a.arm_overlap()
+            loss.backward()
+            how = a.reduce_and_step()
+        assert how == 'bucketed'
+    torch.cuda.synchronize()
+    assert float((a1.flat_param - a2.flat_param).abs().max()) < 5e-5      # bf16-flip noise of two separate forward passes
+    assert int(a1.step_count) == int(a2.step_count) == 3 and float(a2.flat_grad.abs().max()) == 0.0
+    # and captured: the bucket launch on the side stream is recorded as a parallel branch
+    x = torch.randn(4, 1, *shape, device=dev); y = torch.randint(0, 2, (4,), device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        loss, _ = ops.softmax_nll(m2(x), y); a2.arm_overlap(); loss.backward(); a2.reduce_and_step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    import gc
+    del loss
+    gc.collect()
+    graph = torch.cuda.CUDAGraph()
+    before = a2.flat_param.clone()
+    with torch.cuda.graph(graph):
+        loss, _ = ops.softmax_nll(m2(x), y); a2.arm_overlap(); loss.backward(); a2.reduce_and_step()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert not torch.equal(before, a2.flat_param) and float(a2.flat_grad.abs().max()) == 0.0
