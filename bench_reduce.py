@@ -47,7 +47,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--max-mb', type=float, default=1024)
     ap.add_argument('--min-kb', type=float, default=1)
-    ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--iters', type=int, default=10)
+    ap.add_argument('--burst', type=int, default=10, help='back-to-back launches per timed burst (removes host launch skew: '
+                                                           'after the first launch the ranks are aligned by the kernel barrier)')
+    ap.add_argument('--wire16', type=int, default=1, help='also sweep the bf16-wire variants')
     a = ap.parse_args()
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1'); os.environ.setdefault('MASTER_PORT', '29590')
     os.environ.setdefault('RANK', '0'); os.environ.setdefault('WORLD_SIZE', '1'); os.environ.setdefault('LOCAL_RANK', '0')
@@ -65,16 +68,21 @@ def main():
     rows = []
     for nbytes in sizes:
         n = nbytes // 4
-        for variant in (['one_shot', 'two_shot', 'nvls', 'nccl+fused', 'nccl_only'] if world > 1 else ['one_shot']):
+        variants = ['one_shot', 'two_shot', 'nvls', 'nccl+fused', 'nccl_only'] if world > 1 else ['one_shot']
+        if world > 1 and a.wire16:
+            variants += ['two_shot@bf16', 'nvls@bf16']
+        for variant in variants:
             if variant == 'one_shot' and nbytes * world > (1 << 31):
                 continue                               # (S-1)*B ingress: pointless beyond the latency regime
             model = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(n, device=dev))])
             opt = torch.optim.Adam(model.parameters(), lr=1e-3)
             backend = 'nccl' if variant.startswith('nccl') else 'nvlink'
+            kernel_variant, _, wire = variant.partition('@')
             arena = DistArena(model, opt, device=dev, backend=backend,
-                              variant=variant if backend == 'nvlink' else 'auto')
+                              variant=kernel_variant if backend == 'nvlink' else 'auto', grad_dtype=wire or 'f32')
             used = variant
-            iters = a.iters if nbytes <= (64 << 20) else max(3, a.iters // 4)
+            iters = a.iters if nbytes <= (64 << 20) else max(3, a.iters // 3)
+            burst = a.burst if nbytes <= (64 << 20) else max(2, a.burst // 3)
 
             def once():
                 if variant == 'nccl_only':
@@ -90,14 +98,20 @@ def main():
                 dist.barrier(device_ids=[local])
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); once(); e1.record()
+                e0.record()
+                for _b in range(burst):                # back to back on the stream, like the steps of a CUDA graph
+                    once()
+                e1.record()
                 torch.cuda.synchronize()
-                t = torch.tensor([e0.elapsed_time(e1) * 1e3], device=dev)
+                t = torch.tensor([e0.elapsed_time(e1) * 1e3 / burst], device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 times.append(float(t))
             times.sort()
             med = times[len(times) // 2]
+            wire_bytes = nbytes // 2 if wire else nbytes
             roof = roofline_us(nbytes, world, used if used in ('one_shot', 'two_shot', 'nvls') else 'two_shot')
+            if wire:                                   # half the link bytes on the reduce leg, parameters still fp32
+                roof = max(roof * 0.75, 28.0 * (nbytes / 4) / world / (HBM_GBS * 1e3))
             row = {'bytes': nbytes, 'sites': world, 'variant': variant, 'used': used, 'us_median': round(med, 2),
                    'us_min': round(times[0], 2), 'algbw_GBps': round(nbytes / med / 1e3, 2),
                    'roofline_us': round(roof, 2), 'frac_of_roofline': round(roof / med, 4)}

@@ -35,8 +35,8 @@ class PowerSGDPlan:
         self.mats, self.low = [], []          # (param index, n, m, g_off, p_off, q_off) / (param index, g_off, numel)
         p_off = q_off = 0
         for i, (p, off) in enumerate(zip(params, offsets)):
-            if p.dim() >= 2:
-                n, m = p.shape[0], p.numel() // p.shape[0]
+            n, m = (p.shape[0], p.numel() // p.shape[0]) if p.dim() >= 2 else (1, p.numel())
+            if p.dim() >= 2 and min(n, m) > self.rank:      # a rank-r factorisation of a matrix with <= r rows saves nothing
                 self.mats.append((i, n, m, off, p_off, q_off))
                 p_off += n * self.rank
                 q_off += m * self.rank

@@ -121,9 +121,21 @@ def _conv_stack(blocks, x, training):
         cin, cout = conv.in_channels, conv.out_channels
         mom = bn.momentum if bn.momentum is not None else 0.1
         nbt = bn.num_batches_tracked if training else None
+        # A conv bias in front of BatchNorm changes nothing but the tracked mean (batch statistics absorb it, its gradient is
+        # zero): the kernels run bias-free and the running mean is shifted by the bias so state_dicts stay interchangeable.
+        has_bias = conv.bias is not None
+        rm_in = bn.running_mean
+        if has_bias and not training:
+            rm_in = bn.running_mean - conv.bias.detach()
         if h.dim() == 4:                                           # fused first block (1 -> 16)
-            h = ConvBnReluPoolFn.apply(h, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, mom,
-                                       training, 'auto', nbt)
+            if has_bias and training:
+                with _torch.no_grad():
+                    bn.running_mean.sub_(conv.bias.detach())       # track the bias-free mean inside, restore below
+            h = ConvBnReluPoolFn.apply(h, conv.weight, bn.weight, bn.bias, rm_in if not training else bn.running_mean,
+                                       bn.running_var, bn.eps, mom, training, 'auto', nbt)
+            if has_bias and training:
+                with _torch.no_grad():
+                    bn.running_mean.add_(conv.bias.detach())
             have = cout
             continue
         ci_p, co_p = _padded_pair(cin, cout)
@@ -133,19 +145,26 @@ def _conv_stack(blocks, x, training):
             h = h[..., :ci_p]
         h = h.contiguous()
         if (ci_p, co_p) == (cin, cout):
-            h = ConvBnReluPoolFn.apply(h, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, mom,
-                                       training, 'auto', nbt)
+            if has_bias and training:
+                with _torch.no_grad():
+                    bn.running_mean.sub_(conv.bias.detach())
+            h = ConvBnReluPoolFn.apply(h, conv.weight, bn.weight, bn.bias, rm_in if not training else bn.running_mean,
+                                       bn.running_var, bn.eps, mom, training, 'auto', nbt)
+            if has_bias and training:
+                with _torch.no_grad():
+                    bn.running_mean.add_(conv.bias.detach())
         else:
             w = F.pad(conv.weight, (0, 0, 0, 0, 0, 0, 0, ci_p - cin, 0, co_p - cout))
             extra = co_p - cout
             g = _torch.cat([bn.weight, bn.weight.new_ones(extra)]) if extra else bn.weight
             b = _torch.cat([bn.bias, bn.bias.new_zeros(extra)]) if extra else bn.bias
-            rm = _torch.cat([bn.running_mean, bn.running_mean.new_zeros(extra)])
+            shift = conv.bias.detach() if has_bias else 0.0
+            rm = _torch.cat([bn.running_mean - shift, bn.running_mean.new_zeros(extra)])
             rv = _torch.cat([bn.running_var, bn.running_var.new_ones(extra)])
             h = ConvBnReluPoolFn.apply(h, w, g, b, rm, rv, bn.eps, mom, training, 'auto', nbt)
             if training:
                 with _torch.no_grad():
-                    bn.running_mean.copy_(rm[:cout])
+                    bn.running_mean.copy_(rm[:cout] + shift)
                     bn.running_var.copy_(rv[:cout])
         have = co_p                                                # channels >= cout are exactly zero (gamma 1, beta 0, W 0)
         # keep the zero tail if the next block wants it, it is dropped at the end otherwise

@@ -4,10 +4,10 @@ N=${1:-2}; O=gpurun_out/${2:-r2n$N}
 mkdir -p $O
 nvidia-smi topo -m > $O/topo.txt 2>&1
 if [ "${3:-tests}" = "tests" ]; then
-timeout 1500 python -m pytest tests/test_multigpu.py -q --maxfail=20 -p no:cacheprovider > $O/pytest_multigpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_multigpu.log
+timeout 1500 python -m pytest tests/test_multigpu.py -q --maxfail=20 -p no:cacheprovider --timeout 240 > $O/pytest_multigpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_multigpu.log
 tail -30 $O/pytest_multigpu.log
 fi
-run() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 bench.py --gpus $N "${@:3}" > $O/$2.json 2> $O/$2.err; echo "$2 rc=$?"; cat $O/$2.json; }
+run() { timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 bench.py --gpus $N "${@:3}" > $O/$2.json 2> $O/$2.err; echo "$2 rc=$?"; cat $O/$2.json; }
 run 29801 bench_ours --steps 20 --warmup 5
 run 29802 bench_ours_200 --steps 200 --warmup 10
 run 29803 bench_ours_nooverlap --steps 50 --warmup 5 --overlap 0 --skip-e2e

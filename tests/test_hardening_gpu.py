@@ -266,6 +266,8 @@ def test_nativize_user_cnn_matches_torch_forward(dev):
     assert _rel(o_nat, o_ref) < 5e-2, _rel(o_nat, o_ref)
     torch.nn.functional.cross_entropy(o_nat, y).backward()
     for n, p in nat.named_parameters():
+        if n == '0.bias':
+            continue          # a Conv3d bias in front of BatchNorm has no effect and no gradient: the native block ignores it
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
     for (n1, b1), (_, b2) in zip(ref.named_buffers(), nat.named_buffers()):
         assert torch.allclose(b1.float(), b2.float(), rtol=5e-2, atol=5e-3), n1
@@ -292,15 +294,17 @@ def test_nativize_user_cnn_trains(dev):
         loss.backward()
         arena.reduce_and_step()
         losses.append(float(loss))
-    assert sum(losses[-5:]) / 5 < 0.25 < sum(losses[:3]) / 3, (losses[:3], losses[-5:])
+    assert sum(losses[-5:]) / 5 < 0.1 and losses[0] > 5 * (sum(losses[-5:]) / 5), (losses[:3], losses[-5:])
 
 
 def test_bucketed_overlap_with_direct_grad_kernels(dev):
     """The native blocks write gradients straight into the arena and hand autograd None, so bucket launches are driven by
-    ops.linear.notify_grad_written instead of autograd hooks: same parameters as the single launch, also inside a
-    whole-step CUDA graph capture (the side stream becomes a branch of the graph)."""
+    ops.linear.notify_grad_written instead of autograd hooks.
+    (a) identical gradients through both launch schedules -> bit-identical parameters and moments;
+    (b) the real thing: buckets launched on the side stream while backward is still running, eager and captured."""
     from coinstac_dinunet_b200 import ops
     from coinstac_dinunet_b200.models import VBMNet
+    from coinstac_dinunet_b200.ops.linear import notify_grad_written
     from coinstac_dinunet_b200.parallel.arena import DistArena
     shape = (33, 34, 35)
 
@@ -316,9 +320,23 @@ def test_bucketed_overlap_with_direct_grad_kernels(dev):
 
     (m1, a1), (m2, a2) = make(False), make(True)
     g = torch.Generator(device='cpu').manual_seed(5)
+    # (a) same gradient values, two schedules
+    for step in range(3):
+        grads = torch.randn(a1.numel, generator=g).to(dev)
+        a1.flat_grad.copy_(grads); a2.flat_grad.copy_(grads)
+        a1.reduce_and_step()
+        a2.arm_overlap()
+        for p in reversed(a2.params):                      # "backward" order: every parameter reports its gradient final
+            notify_grad_written(p)
+        assert a2.reduce_and_step() == 'bucketed'
+    torch.cuda.synchronize()
+    assert torch.equal(a1.flat_param, a2.flat_param) and torch.equal(a1.m, a2.m) and torch.equal(a1.v, a2.v)
+    assert int(a1.step_count) == int(a2.step_count) == 3 and float(a2.flat_grad.abs().max()) == 0.0
+    # (b) real backward passes with the buckets in flight
+    start = a2.flat_param.clone()
     for step in range(3):
         y = torch.randint(0, 2, (4,), generator=g).to(dev)
-        x = torch.randn(4, 1, *shape, generator=g).to(dev)
+        x = torch.randn(4, 1, *shape, generator=g).to(dev) + 0.5 * (y.float() * 2 - 1).view(-1, 1, 1, 1, 1).to(dev)
         for m, a in ((m1, a1), (m2, a2)):
             loss, _ = ops.softmax_nll(m(x), y)
             a.arm_overlap()
@@ -326,9 +344,10 @@ def test_bucketed_overlap_with_direct_grad_kernels(dev):
             how = a.reduce_and_step()
         assert how == 'bucketed'
     torch.cuda.synchronize()
-    assert float((a1.flat_param - a2.flat_param).abs().max()) < 5e-5      # bf16-flip noise of two separate forward passes
-    assert int(a1.step_count) == int(a2.step_count) == 3 and float(a2.flat_grad.abs().max()) == 0.0
-    # and captured: the bucket launch on the side stream is recorded as a parallel branch
+    u1, u2 = (a1.flat_param - start).flatten(), (a2.flat_param - start).flatten()
+    assert torch.nn.functional.cosine_similarity(u1, u2, dim=0) > 0.9        # same trajectory up to bf16-flip noise
+    assert int(a2.step_count) == 6 and float(a2.flat_grad.abs().max()) == 0.0
+    # and captured: the bucket launch on the side stream is recorded as a parallel branch of the graph
     x = torch.randn(4, 1, *shape, device=dev); y = torch.randint(0, 2, (4,), device=dev)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
