@@ -284,7 +284,8 @@ class ConvBnReluPoolFn(_torch.autograd.Function):
             ctx.first, ctx.backend, ctx.training, ctx.fused_shape = first, backend, training, shape
             return p
         ctx.fused_shape = None
-        y, stats = conv3d_fwd(x, conv_w, backend, want_stats=bool(training), stats_out=stats_buf)
+        res = conv3d_fwd(x, conv_w, backend, want_stats=bool(training), stats_out=stats_buf)
+        y, stats = res if training else (res, None)
         N, D, H, W, C = y.shape
         if training:
             if stats is None:

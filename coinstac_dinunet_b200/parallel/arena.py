@@ -437,7 +437,7 @@ class DistArena:
                 buckets.append({'offset': start, 'numel': stop - start, 'params': members, 'pending': len(members)})
                 stop, members = start, []
         assert sum(b['numel'] for b in buckets) == self.numel and ends
-        self._overlap = {'buckets': buckets, 'armed': False, 'launched': set(),
+        self._overlap = {'buckets': buckets, 'armed': False, 'launched': set(), 'seen': set(),
                          'stream': _torch.cuda.Stream(self.device), 'owner': {}}
         for b_ix, b in enumerate(buckets):
             for i in b['params']:
@@ -453,6 +453,7 @@ class DistArena:
         if ov:
             ov['armed'] = True
             ov['launched'] = set()
+            ov['seen'] = set()
             for b in ov['buckets']:
                 b['pending'] = len(b['params'])
 
@@ -478,6 +479,9 @@ class DistArena:
         ov = self._overlap
         if not ov['armed']:
             return
+        if param_ix in ov['seen']:
+            return      # one count per parameter and step: autograd runs AccumulateGrad (and its hooks) even for the undefined
+        ov['seen'].add(param_ix)   # gradients of direct-mode kernels, which have already reported through notify_grad_written
         b_ix = ov['owner'][param_ix]
         b = ov['buckets'][b_ix]
         b['pending'] -= 1

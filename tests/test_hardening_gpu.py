@@ -346,7 +346,8 @@ def test_bucketed_overlap_with_direct_grad_kernels(dev):
     torch.cuda.synchronize()
     u1, u2 = (a1.flat_param - start).flatten(), (a2.flat_param - start).flatten()
     assert torch.nn.functional.cosine_similarity(u1, u2, dim=0) > 0.9        # same trajectory up to bf16-flip noise
-    assert int(a2.step_count) == 6 and float(a2.flat_grad.abs().max()) == 0.0
+    dirty = {n: float(p.grad.abs().max()) for n, p in m2.named_parameters() if float(p.grad.abs().max()) != 0.0}
+    assert int(a2.step_count) == 6 and not dirty, dirty
     # and captured: the bucket launch on the side stream is recorded as a parallel branch of the graph
     x = torch.randn(4, 1, *shape, device=dev); y = torch.randint(0, 2, (4,), device=dev)
     side = torch.cuda.Stream()
