@@ -58,6 +58,16 @@ class DistEngine:
         init_process_group()
         self.group = group
         self.rank, self.world = _dist.get_rank(group), _dist.get_world_size(group)
+        # The JSON control plane rides a gloo group when the data plane is NCCL: object collectives over NCCL stage
+        # their pickles through device tensors and synchronise the stream - a millisecond per round that the (tiny)
+        # messages do not need.
+        self.ctl = group
+        try:
+            if _dist.get_backend(group) == 'nccl' and self.world > 1 and _os.environ.get('COINN_CTL_GLOO', '1') == '1':
+                ranks = _dist.get_process_group_ranks(group) if group is not None else None
+                self.ctl = _dist.new_group(ranks=ranks, backend='gloo')
+        except Exception:
+            self.ctl = group
         self.work_dir = str(work_dir)
         self.site_ids = [f'local{i}' for i in range(self.world)]
         self.site = self.site_ids[self.rank]
@@ -75,7 +85,7 @@ class DistEngine:
         t0 = _time.time()
         out = local_fn(self.site, self.cache, self.input, self.state)['output']
         gathered = [None] * self.world if self.rank == 0 else None
-        _dist.gather_object(_jsonish(out), gathered, dst=0, group=self.group)  # doubles as file barrier
+        _dist.gather_object(_jsonish(out), gathered, dst=0, group=self.ctl)    # doubles as file barrier
         payload = [None]
         if self.rank == 0:
             for st in self.all_site_states:
@@ -89,7 +99,7 @@ class DistEngine:
             if self.clear_transfer:
                 _clear_files(self.remote_state['transferDirectory'])
             payload = [(_jsonish(res['output']), bool(res.get('success')))]
-        _dist.broadcast_object_list(payload, src=0, group=self.group)
+        _dist.broadcast_object_list(payload, src=0, group=self.ctl)
         remote_out, success = payload[0]
         self.input = dict(remote_out)
         self.trace.append({'site': (str(out.get('phase')), str(out.get('mode'))),

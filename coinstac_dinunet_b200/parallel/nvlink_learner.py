@@ -164,6 +164,13 @@ class NvlinkLearner(COINNLearner):
             out.update(**flags)
         return its, out
 
+    def _end_of_round_cursor(self):
+        """The round IS the epoch: report it finished regardless of where the local cursor is and start the next round
+        with a fresh (re-shuffled) loader.  With an explicit ``steps_per_round`` the site streams instead: the loader
+        iterator - and the batches its prefetcher has already staged on the device - carry over into the next round."""
+        if not self.cache.get('steps_per_round'):
+            self.cache['cursor'] = 0
+
     def _graphed_round(self, steps):
         """``cache['cuda_graph']``: capture the whole step once, then replay it ``steps`` times."""
         from .graph_step import GraphedStep
@@ -198,7 +205,7 @@ class NvlinkLearner(COINNLearner):
         if graphable:
             it = self._graphed_round(self._steps_this_round())
             self.arena.check_health()                     # barrier watchdog: a site that never arrived raises here
-            self.cache['cursor'] = 0
+            self._end_of_round_cursor()
             out['mode'] = Mode.VALIDATION_WAITING
             out['fused_steps'] = self.arena.steps_done
             return it, out
@@ -227,8 +234,7 @@ class NvlinkLearner(COINNLearner):
             from ..utils.profiling import site_profile
             out['profile'] = site_profile(self.cache, timer, key='profile_log')
         self.arena.check_health()
-        # the round IS the epoch: report it finished regardless of where the local cursor is
-        self.cache['cursor'] = 0
+        self._end_of_round_cursor()
         out['mode'] = Mode.VALIDATION_WAITING
         out['fused_steps'] = self.arena.steps_done
         return scores.result(), out

@@ -366,3 +366,38 @@ def test_bucketed_overlap_with_direct_grad_kernels(dev):
     graph.replay()
     torch.cuda.synchronize()
     assert not torch.equal(before, a2.flat_param) and float(a2.flat_grad.abs().max()) == 0.0
+
+
+def test_fp8_training_tracks_bf16_over_200_steps(dev):
+    """BASELINE config 4 numerics: VBMNet with MX-FP8 block-scaled conv fprop/dgrad (blocks 3-5) vs the bf16 kernels on the
+    same stream of batches, 200 fused-Adam steps: both learn the task and the smoothed loss curves stay together."""
+    from coinstac_dinunet_b200 import ops
+    from coinstac_dinunet_b200.models import VBMNet
+    from coinstac_dinunet_b200.ops import conv3d as c3
+    from coinstac_dinunet_b200.parallel.arena import DistArena
+    shape = (33, 34, 35)
+
+    def train(backend):
+        torch.manual_seed(0)
+        model = VBMNet(input_shape=shape, native=True, conv_backend=backend).to(dev)
+        arena = DistArena(model, torch.optim.Adam(model.parameters(), lr=5e-4), device=dev, backend='nvlink')
+        g = torch.Generator(device='cpu').manual_seed(1)
+        model.train()
+        losses, used = [], set()
+        for step in range(200):
+            yb = torch.randint(0, 2, (8,), generator=g).to(dev)
+            xb = torch.randn(8, 1, *shape, generator=g).to(dev) + (yb.float() * 2 - 1).view(-1, 1, 1, 1, 1) * 0.3
+            loss, _ = ops.softmax_nll(model(xb), yb)
+            used.add(c3.last_impl)
+            loss.backward()
+            arena.reduce_and_step()
+            losses.append(float(loss.detach()))
+        return torch.tensor(losses), used
+
+    bf16, _ = train('auto')
+    fp8, used = train('fp8')
+    assert 'mxfp8' in used
+    smooth = lambda t: t.view(20, 10).mean(1)
+    a, b = smooth(bf16), smooth(fp8)
+    assert float(a[-3:].mean()) < 0.15 and float(b[-3:].mean()) < 0.15, (a.tolist(), b.tolist())
+    assert float((a - b).abs().max()) < 0.2, (a.tolist(), b.tolist())
