@@ -196,22 +196,32 @@ __device__ __forceinline__ float segmat_at(const SegMat& A, int row, int col) {
 constexpr int LR_MAX_N = 96;
 constexpr int GRAM_ROWS = 64;
 
-// out[n, n] += A^T A over a chunk of rows (out zeroed by the caller)
-__global__ void __launch_bounds__(256) gram_seg_kernel(SegMat A, float* __restrict__ out) {
+// part[chunk][n][n] = A_chunk^T A_chunk for GRAM_ROWS rows per CTA; gram_reduce_kernel then adds the chunks in a FIXED order.
+// No atomics: every site re-compresses the same gathered factors redundantly and the replicas must stay bit-identical.
+__global__ void __launch_bounds__(256) gram_seg_kernel(SegMat A, float* __restrict__ part) {
     extern __shared__ float tile[];                      // [GRAM_ROWS][n]
     const int n = A.n;
     const int row0 = blockIdx.x * GRAM_ROWS;
     const int rows = min(GRAM_ROWS, A.rows - row0);
     for (int i = threadIdx.x; i < rows * n; i += blockDim.x) tile[i] = segmat_at(A, row0 + i / n, i % n);
     __syncthreads();
+    float* out = part + (long long)blockIdx.x * n * n;
     for (int o = threadIdx.x; o < n * n; o += blockDim.x) {
         const int i = o / n, j = o % n;
         if (j < i) continue;                              // symmetric: compute the upper triangle, mirror
         float s = 0.f;
         for (int rr = 0; rr < rows; ++rr) s = fmaf(tile[rr * n + i], tile[rr * n + j], s);
-        atomicAdd(out + (long long)i * n + j, s);
-        if (j != i) atomicAdd(out + (long long)j * n + i, s);
+        out[(long long)i * n + j] = s;
+        out[(long long)j * n + i] = s;
     }
+}
+
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ part, int chunks, int nn, float* __restrict__ out) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nn) return;
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += part[(long long)c * nn + o];
+    out[o] = s;
 }
 
 // Top-k singular triplets of G = B C^T from the n x n Gram matrices Gb = B^T B, Gc = C^T C.
@@ -442,15 +452,18 @@ static SegMat mk_seg(const float* base, long long seg_stride, int rows, int n, i
     SegMat A; A.base = base; A.seg_stride = seg_stride; A.rows = rows; A.n = n; A.kseg = kseg > 0 ? kseg : n; return A;
 }
 
-// out [n, n] must be zeroed
-COINN_API int coinn_gram_seg(const float* base, long long seg_stride, int rows, int n, int kseg, float* out, void* stream) {
-    if (n < 1 || n > LR_MAX_N) return (int)cudaErrorInvalidValue;
-    if (rows == 0) return 0;
+// out [n, n] = A^T A (deterministic two-stage sum); scratch: >= ceil(rows / 64) * n * n floats
+COINN_API int coinn_gram_seg(const float* base, long long seg_stride, int rows, int n, int kseg, float* out, float* scratch, void* stream) {
+    if (n < 1 || n > LR_MAX_N || rows < 1) return (int)cudaErrorInvalidValue;
+    const int chunks = (rows + GRAM_ROWS - 1) / GRAM_ROWS;
     const int smem = GRAM_ROWS * n * (int)sizeof(float);
-    gram_seg_kernel<<<(rows + GRAM_ROWS - 1) / GRAM_ROWS, 256, smem, ST(stream)>>>(mk_seg(base, seg_stride, rows, n, kseg), out);
+    gram_seg_kernel<<<chunks, 256, smem, ST(stream)>>>(mk_seg(base, seg_stride, rows, n, kseg), scratch);
+    COINN_CHECK_LAUNCH();
+    gram_reduce_kernel<<<(n * n + 255) / 256, 256, 0, ST(stream)>>>(scratch, chunks, n * n, out);
     COINN_CHECK_LAUNCH();
     return 0;
 }
+COINN_API int coinn_gram_rows_per_chunk() { return GRAM_ROWS; }
 
 COINN_API int coinn_lowrank_eig(const float* Gb, const float* Gc, int n, int k, int iters, float tol, float* X, float* Y, void* stream) {
     if (n < 1 || n > LR_MAX_N || k < 1 || k > 16 || k > n) return (int)cudaErrorInvalidValue;

@@ -149,11 +149,14 @@ def lowrank_factor(B, C, rank, iters, tol, b_seg=None, c_seg=None, scale=1.0, ou
     assert n == n2, (n, n2)
     dev = bt.device
     k = max(1, min(int(rank), rows_b, rows_c, n))
-    grams = _torch.zeros(2, n, n, dtype=_torch.float32, device=dev)
+    grams = _torch.empty(2, n, n, dtype=_torch.float32, device=dev)
     coef = _torch.empty(2, n, k, dtype=_torch.float32, device=dev)
+    chunk = lib.coinn_gram_rows_per_chunk()
+    scratch = _torch.empty((-(-max(rows_b, rows_c) // chunk)) * n * n, dtype=_torch.float32, device=dev)
     sp = _sp(dev)
-    _nat.check(lib.coinn_gram_seg(bt.data_ptr(), int(bs), rows_b, n, bk, grams[0].data_ptr(), sp), 'gram_seg[B]')
-    _nat.check(lib.coinn_gram_seg(ct.data_ptr(), int(cs), rows_c, n, ck, grams[1].data_ptr(), sp), 'gram_seg[C]')
+    # deterministic two-stage Gram sums (no atomics): every site repeats the re-compression and must get the same bits
+    _nat.check(lib.coinn_gram_seg(bt.data_ptr(), int(bs), rows_b, n, bk, grams[0].data_ptr(), scratch.data_ptr(), sp), 'gram_seg[B]')
+    _nat.check(lib.coinn_gram_seg(ct.data_ptr(), int(cs), rows_c, n, ck, grams[1].data_ptr(), scratch.data_ptr(), sp), 'gram_seg[C]')
     _nat.check(lib.coinn_lowrank_eig(grams[0].data_ptr(), grams[1].data_ptr(), n, k, int(iters), float(tol),
                                      coef[0].data_ptr(), coef[1].data_ptr(), sp), 'lowrank_eig')
     left = out_left if out_left is not None else _torch.empty(rows_b, k, dtype=_torch.float32, device=dev)
@@ -163,7 +166,7 @@ def lowrank_factor(B, C, rank, iters, tol, b_seg=None, c_seg=None, scale=1.0, ou
                                          float(scale), sp), 'skinny_gemm[B]')
     _nat.check(lib.coinn_skinny_gemm_seg(ct.data_ptr(), int(cs), rows_c, n, ck, coef[1].data_ptr(), k, right.data_ptr(),
                                          1.0, sp), 'skinny_gemm[C]')
-    _bump(5)
+    _bump(7)
     return left, right
 
 

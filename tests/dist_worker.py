@@ -23,7 +23,7 @@ def scenario_protocol(work, opts):
                 start_powerSGD_iter=2, matrix_approximation_rank=2, cuda_graph=opts.get('cuda_graph') == '1',
                 epochs=int(opts.get('epochs', 2)), reduce_variant=opts.get('reduce_variant', 'auto'),
                 overlap_backward=opts.get('overlap') == '1', bucket_bytes=int(opts.get('bucket_bytes', 64 << 10)),
-                precision_bits=int(opts.get('precision_bits', 32)),
+                precision_bits=int(opts.get('precision_bits', 32)), dad_reduction_rank=int(opts.get('dad_rank', 10)),
                 gpus=[int(os.environ.get('LOCAL_RANK', 0))] if torch.cuda.is_available() else None)
     eng = DistEngine(work, inputspec=spec)
     # count torch.distributed collectives issued INSIDE a compressed / rankDAD optimizer step (the device data plane

@@ -45,6 +45,14 @@ def test_rankdad_protocol_over_nvlink(tmp_path):
     assert res['compressed_steps'] > 0 and res['collectives_in_steps'] == 0, res
 
 
+def test_rankdad_recompression_is_bit_identical_on_every_site(tmp_path):
+    """rank 1 per site: S * k > rank already at two sites, so every site re-compresses the gathered factors redundantly -
+    the Gram sums are deterministic (two-stage, no atomics), replicas must not drift (they did at 8 sites with atomics)."""
+    res = run_workers('protocol', tmp_path, nproc=_n(), port=29712, extra=['transport=nvlink', 'agg_engine=rankDAD', 'dad_rank=1'])
+    assert res['backend'] == 'nvlink' and res['trace'][-2] == 'success' and res['replicas_identical'], res
+    assert res['compressed_steps'] > 0 and res['collectives_in_steps'] == 0, res
+
+
 def test_bucketed_overlap_matches_single_launch(tmp_path):
     res = run_workers('overlap', tmp_path, nproc=_n(), port=29705)
     for r in res['results']:
