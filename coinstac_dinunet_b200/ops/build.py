@@ -58,20 +58,44 @@ def _compile(src, verbose):
     return obj, True
 
 
+LAST_BUILD = {}      # what the most recent build() in this process did (also written to profiles/build_record.json)
+
+
 def build(verbose=False, force=False):
+    """Compile every csrc/*.cu for sm_100a and link ``_b200_ops.so``.  Objects are cached by the sha1 of (source, headers,
+    flags); ``force=True`` or ``COINN_FORCE_REBUILD=1`` recompiles everything from scratch.  What happened - per source
+    "compiled" or "cached", the nvcc version, the flags, the sha256 of the library - is recorded in ``LAST_BUILD``."""
+    import time
     os.makedirs(OBJ_DIR, exist_ok=True)
+    force = force or os.environ.get('COINN_FORCE_REBUILD') == '1'
     if force:
         for f in os.listdir(OBJ_DIR):
             os.remove(os.path.join(OBJ_DIR, f))
     srcs = sources()
+    t0 = time.time()
     with ThreadPoolExecutor(max_workers=min(8, len(srcs) or 1)) as ex:
         results = list(ex.map(lambda s: _compile(s, verbose), srcs))
     objs = [o for o, _ in results]
-    if any(changed for _, changed in results) or not os.path.exists(LIB):
+    relinked = any(changed for _, changed in results) or not os.path.exists(LIB)
+    if relinked:
         cmd = [NVCC, *ARCH, '-shared', '-o', LIB, *objs, '-lcudart']
         if verbose:
             print(' '.join(cmd), flush=True)
         subprocess.run(cmd, check=True)
+    try:
+        ver = subprocess.run([NVCC, '--version'], capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    except Exception:
+        ver = 'unknown'
+    with open(LIB, 'rb') as fp:
+        lib_sha = hashlib.sha256(fp.read()).hexdigest()
+    LAST_BUILD.clear()
+    LAST_BUILD.update({
+        'mode': 'from_scratch' if all(c for _, c in results) else ('incremental' if relinked else 'cached'),
+        'forced': bool(force), 'seconds': round(time.time() - t0, 2), 'nvcc': ver, 'arch': ARCH[1],
+        'flags': {'default': FLAGS, 'exact_math_files': sorted(EXACT_MATH)},
+        'sources': {os.path.basename(s): ('compiled' if c else 'cached') for s, (_, c) in zip(srcs, results)},
+        'relinked': bool(relinked), 'library': os.path.relpath(LIB, os.path.dirname(os.path.dirname(HERE))),
+        'library_sha256': lib_sha, 'library_bytes': os.path.getsize(LIB)})
     return LIB
 
 

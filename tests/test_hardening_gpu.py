@@ -81,7 +81,7 @@ def test_native_vbmnet_matches_bf16_emulated_oracle(dev):
 
     * the well-conditioned quantities - logits, head / classifier gradients, last block's BatchNorm - agree to 2e-2;
     * the conv-stack gradients of a randomly initialised BN network are chaotic in the rounding noise (measured on B200,
-      profiles/r2_determinism.txt: a 1e-7 perturbation of the oracle itself moves the first block's gradient by 1e-3; the
+      profiles/r2/determinism.txt: a 1e-7 perturbation of the oracle itself moves the first block's gradient by 1e-3; the
       1e-6 run-to-run jitter of fp32-atomic BatchNorm sums moves the native one by several percent although every kernel
       is bit-reproducible on identical inputs).  For those the bound is 3x the native run-to-run spread + 2e-2: the
       kernels must sit inside their own noise envelope around the oracle."""
