@@ -306,3 +306,27 @@ def test_nativize_plans_user_models_without_touching_state_dict():
     # strides / kernel sizes the kernels do not implement stay on the torch path
     other = nn.Sequential(nn.Conv3d(4, 8, 5, padding=2), nn.BatchNorm3d(8), nn.ReLU(), nn.MaxPool3d(2))
     assert not isinstance(nativize(other), NativeSequential)
+
+
+def test_affinity_helpers_parse_topology_and_never_raise():
+    from coinstac_dinunet_b200.utils import affinity
+    assert affinity._parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    assert affinity._parse_cpulist('') == set()
+    rep = affinity.pin_to_gpu(0)            # no GPU here: must report "not pinned" instead of failing
+    assert rep['gpu'] == 0 and rep['pinned'] in (False, True)
+
+
+def test_custom_example_model_is_nativizable():
+    import importlib.util, os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('custom_local', os.path.join(here, 'examples', 'custom', 'local.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from coinstac_dinunet_b200.ops import nativize
+    report = []
+    net = nativize(mod.MyNet((16, 16, 16)), report=report)
+    kinds = {r[1] for r in report}
+    assert {'conv_stack', 'linear_bn_relu', 'linear'} <= kinds
+    import torch
+    net.eval()
+    assert net(torch.randn(2, 1, 16, 16, 16)).shape == (2, 2)
