@@ -68,6 +68,7 @@ class DistEngine:
                 self.ctl = _dist.new_group(ranks=ranks, backend='gloo')
         except Exception:
             self.ctl = group
+        self._mailbox = self._open_mailbox()
         self.work_dir = str(work_dir)
         self.site_ids = [f'local{i}' for i in range(self.world)]
         self.site = self.site_ids[self.rank]
@@ -81,12 +82,62 @@ class DistEngine:
         self.all_site_states = [node_state(self.work_dir, s) for s in self.site_ids] if self.rank == 0 else None
         self.trace, self.round, self.timings = [], 0, []
 
+    def _open_mailbox(self):
+        """Single-node runs exchange the per-round JSON through shared memory (``engine/shm_plane.py``); multi-node runs,
+        or ``COINN_CTL_SHM=0``, keep the ``torch.distributed`` object collectives."""
+        import atexit
+        if self.world == 1 or _os.environ.get('COINN_CTL_SHM', '1') != '1':
+            return None
+        local_world = int(_os.environ.get('LOCAL_WORLD_SIZE', self.world))
+        try:
+            hosts = [None] * self.world
+            _dist.all_gather_object(hosts, _os.uname().nodename, group=self.ctl)
+            if local_world != self.world or len(set(hosts)) != 1:
+                return None
+            from .shm_plane import ShmMailbox
+            box, mb, ok = [None], None, True
+            if self.rank == 0:
+                try:
+                    mb = ShmMailbox(None, 0, self.world, create=True)
+                    box[0] = mb.name
+                except Exception:
+                    ok = False
+            _dist.broadcast_object_list(box, src=0, group=self.ctl)
+            if self.rank != 0 and box[0] is not None:
+                try:
+                    mb = ShmMailbox(box[0], self.rank, self.world, create=False)
+                except Exception:
+                    ok = False
+            votes = [None] * self.world                     # every rank must have the segment mapped, or nobody uses it
+            _dist.all_gather_object(votes, bool(ok and mb is not None), group=self.ctl)
+            if not all(votes):
+                if mb is not None:
+                    mb.close()
+                return None
+            atexit.register(mb.close)
+            return mb
+        except Exception:
+            return None
+
+    def _gather(self, obj):
+        if self._mailbox is not None:
+            return self._mailbox.gather(obj)
+        gathered = [None] * self.world if self.rank == 0 else None
+        _dist.gather_object(obj, gathered, dst=0, group=self.ctl)
+        return gathered
+
+    def _broadcast(self, payload):
+        if self._mailbox is not None:
+            return self._mailbox.broadcast(payload)
+        box = [payload]
+        _dist.broadcast_object_list(box, src=0, group=self.ctl)
+        return box[0]
+
     def step(self, local_fn, remote_fn):
         t0 = _time.time()
         out = local_fn(self.site, self.cache, self.input, self.state)['output']
-        gathered = [None] * self.world if self.rank == 0 else None
-        _dist.gather_object(_jsonish(out), gathered, dst=0, group=self.ctl)    # doubles as file barrier
-        payload = [None]
+        gathered = self._gather(_jsonish(out))                              # doubles as file barrier
+        payload = None
         if self.rank == 0:
             for st in self.all_site_states:
                 src = st['transferDirectory']
@@ -98,9 +149,8 @@ class DistEngine:
                 _copy_tree_flat(self.remote_state['transferDirectory'], st['baseDirectory'])
             if self.clear_transfer:
                 _clear_files(self.remote_state['transferDirectory'])
-            payload = [(_jsonish(res['output']), bool(res.get('success')))]
-        _dist.broadcast_object_list(payload, src=0, group=self.ctl)
-        remote_out, success = payload[0]
+            payload = (_jsonish(res['output']), bool(res.get('success')))
+        remote_out, success = self._broadcast(payload)
         self.input = dict(remote_out)
         self.trace.append({'site': (str(out.get('phase')), str(out.get('mode'))),
                            'remote': str(remote_out.get('phase'))})
