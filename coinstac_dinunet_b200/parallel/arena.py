@@ -313,9 +313,9 @@ class DistArena:
         if v == 'auto':
             if self.world == 1 or nbytes <= _conf.ONE_SHOT_MAX_BYTES:
                 v = 'one_shot'
-            elif self._exchange_buf.multicast_ptr and self.param_buf.multicast_ptr:
-                v = 'nvls'
-            else:
+            elif self.world > 2 and self._exchange_buf.multicast_ptr and self.param_buf.multicast_ptr:
+                v = 'nvls'          # in-switch reduction pays from 4 sites up; at 2 sites two-shot is as fast or faster
+            else:                   # (profiles/r2/reduce_sweep_n2.json: 60 vs 77 us at 16 MB, 2.0 vs 2.8 ms at 1 GB)
                 v = 'two_shot'
         if v == 'nvls' and not (self._exchange_buf.multicast_ptr and self.param_buf.multicast_ptr):
             v = 'two_shot'
