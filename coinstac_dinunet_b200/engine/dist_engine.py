@@ -98,14 +98,16 @@ class DistEngine:
             box, mb, ok = [None], None, True
             if self.rank == 0:
                 try:
-                    mb = ShmMailbox(None, 0, self.world, create=True)
+                    mb = ShmMailbox(None, 0, self.world, create=True,
+                                    slot_bytes=int(_os.environ.get('COINN_CTL_SLOT_BYTES', 1 << 20)))
                     box[0] = mb.name
                 except Exception:
                     ok = False
             _dist.broadcast_object_list(box, src=0, group=self.ctl)
             if self.rank != 0 and box[0] is not None:
                 try:
-                    mb = ShmMailbox(box[0], self.rank, self.world, create=False)
+                    mb = ShmMailbox(box[0], self.rank, self.world, create=False,
+                                    slot_bytes=int(_os.environ.get('COINN_CTL_SLOT_BYTES', 1 << 20)))
                 except Exception:
                     ok = False
             votes = [None] * self.world                     # every rank must have the segment mapped, or nobody uses it
@@ -115,6 +117,21 @@ class DistEngine:
                     mb.close()
                 return None
             atexit.register(mb.close)
+            grp = self.ctl
+
+            def send_big(obj, peer):
+                _dist.send_object_list([obj], dst=peer, group=grp)
+
+            def recv_big(peer):
+                box = [None]
+                _dist.recv_object_list(box, src=peer, group=grp)
+                return box[0]
+
+            def bcast_big(obj):
+                box = [obj]
+                _dist.broadcast_object_list(box, src=0, group=grp)
+                return box[0]
+            mb.send_big, mb.recv_big, mb.bcast_big = send_big, recv_big, bcast_big
             return mb
         except Exception:
             return None

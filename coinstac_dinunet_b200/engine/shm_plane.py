@@ -15,14 +15,23 @@ from multiprocessing import shared_memory as _shm
 _HDR = 16
 
 
+_OVERSIZE = '__coinn_via_torch_distributed__'
+
+
 class ShmMailbox:
-    def __init__(self, name, rank, world, slot_bytes=4 << 20, create=False, timeout_s=1800.0):
+    """``oversize(obj, peer)`` / ``fetch(peer)``: callbacks that move ONE message over ``torch.distributed`` point-to-point when
+    it does not fit a slot (the mailbox then only carries a marker) - set by ``DistEngine``; without them an oversized message
+    raises."""
+
+    def __init__(self, name, rank, world, slot_bytes=1 << 20, create=False, timeout_s=1800.0):
         self.rank, self.world, self.slot, self.timeout = rank, world, int(slot_bytes), float(timeout_s)
+        self.send_big = self.recv_big = self.bcast_big = None
         size = (world + 1) * self.slot
         self.mem = _shm.SharedMemory(name=name, create=create, size=size if create else 0)
         self.owner = create
         if create:
-            self.mem.buf[:size] = bytes(size)
+            for slot in range(world + 1):              # only the headers: pages of /dev/shm are touched when first written
+                self.mem.buf[slot * self.slot:slot * self.slot + _HDR] = bytes(_HDR)
         else:
             try:    # attaching processes must not let their resource tracker unlink a segment they do not own
                 from multiprocessing import resource_tracker
@@ -39,12 +48,16 @@ class ShmMailbox:
     # ------------------------------------------------------------------ raw slots
     def _write(self, slot, seq, obj):
         data = _pickle.dumps(obj, protocol=_pickle.HIGHEST_PROTOCOL)
-        if len(data) + _HDR > self.slot:
-            raise ValueError(f'control-plane message of {len(data)} bytes does not fit the {self.slot}-byte mailbox slot')
+        big = len(data) + _HDR > self.slot
+        if big:
+            if self.send_big is None:
+                raise ValueError(f'control-plane message of {len(data)} bytes does not fit the {self.slot}-byte mailbox slot')
+            data = _pickle.dumps(_OVERSIZE)
         base = slot * self.slot
         self.mem.buf[base + _HDR:base + _HDR + len(data)] = data
         _struct.pack_into('<Q', self.mem.buf, base + 8, len(data))
         _struct.pack_into('<Q', self.mem.buf, base, seq)            # publish last
+        return big
 
     def _read(self, slot, seq):
         base = slot * self.slot
@@ -65,18 +78,30 @@ class ShmMailbox:
     def gather(self, obj):
         """Every rank posts ``obj``; rank 0 returns the list of all ranks' objects, the others ``None``."""
         self.seq += 1
-        self._write(self.rank, self.seq, obj)
+        if self._write(self.rank, self.seq, obj):
+            if self.rank != 0:
+                self.send_big(obj, 0)                  # the marker is posted: rank 0 will ask for the payload point-to-point
         if self.rank != 0:
             return None
-        return [self._read(r, self.seq) for r in range(self.world)]
+        out = []
+        for r in range(self.world):
+            got = self._read(r, self.seq)
+            if isinstance(got, str) and got == _OVERSIZE:
+                got = obj if r == 0 else self.recv_big(r)
+            out.append(got)
+        return out
 
     def broadcast(self, obj=None):
         """Rank 0 posts ``obj`` in the answer slot; every rank returns it."""
         self.answers += 1
         if self.rank == 0:
-            self._write(self.world, self.answers, obj)
+            if self._write(self.world, self.answers, obj):
+                self.bcast_big(obj)
             return obj
-        return self._read(self.world, self.answers)
+        got = self._read(self.world, self.answers)
+        if isinstance(got, str) and got == _OVERSIZE:
+            got = self.bcast_big(None)
+        return got
 
     def close(self):
         try:

@@ -38,3 +38,12 @@ def test_pretrained_weights_broadcast_without_files_on_device_transports(tmp_pat
     assert res['csv'] and res['trace'][-2] == 'success' and res['replicas_identical']
     assert 'pre_computation' in [str(t).split('.')[-1].lower() for t in res['trace']]
     assert res['weights_broadcast'] == 'device'
+
+
+def test_control_plane_mailbox_handles_oversized_messages(tmp_path):
+    """Per-round JSON goes through the shared-memory mailbox; a message that does not fit a slot (here: 256-byte slots, so
+    nearly every message) transparently travels point-to-point over torch.distributed instead - same run, same result."""
+    res = run_workers('protocol', tmp_path, port=29615, extra=['agg_engine=dSGD'], env={'COINN_CTL_SLOT_BYTES': '256'})
+    assert res['csv'] and res['trace'][-2] == 'success' and res['replicas_identical']
+    res2 = run_workers('protocol', tmp_path / 'gloo', port=29616, extra=['agg_engine=dSGD'], env={'COINN_CTL_SHM': '0'})
+    assert res2['trace'] == res['trace'] and res2['rounds'] == res['rounds']      # (the fold seed is drawn per run)
