@@ -170,6 +170,42 @@ def lowrank_factor(B, C, rank, iters, tol, b_seg=None, c_seg=None, scale=1.0, ou
     return left, right
 
 
+def lowrank_factor_reference(B, C, rank, iters, tol):
+    """PyTorch oracle of ``lowrank_factor`` - the same algorithm, step for step (runs anywhere, documents the kernel):
+    with ``Gb = B^T B`` and ``Gc = C^T C`` (both ``[n, n]``) every left singular vector of ``G = B C^T`` is ``u = B x`` and
+    ``G G^T u = B (Gc Gb x)``, so power iteration, normalisation (``x^T Gb x = 1``) and deflation against the previous vectors
+    (``x -= (x_p^T Gb x) x_p``) all happen on n-vectors; ``sigma^2 = (Gb x)^T Gc (Gb x)``, the right vector is ``C (Gb x) / sigma``.
+    Returns (left * sigma [rowsB, k], right [rowsC, k])."""
+    B, C = B.double(), C.double()
+    n = B.shape[1]
+    k = max(1, min(int(rank), B.shape[0], C.shape[0], n))
+    Gb, Gc = B.t() @ B, C.t() @ C
+    X, Y, prev, prevw, sigma0 = [], [], [], [], None
+    idx = _torch.arange(1, n + 1, dtype=_torch.float64)
+    for c in range(k):
+        x = 0.5 + 0.5 * _torch.sin(12.9898 * idx + 78.233 * (c + 1))
+        for it in range(int(iters) + 1):
+            for xp, wp in zip(prev, prevw):
+                x = x - (wp @ x) * xp
+            w = Gb @ x
+            nrm2 = float(x @ w)
+            inv = nrm2 ** -0.5 if nrm2 > 1e-30 else 0.0
+            x, w = x * inv, w * inv
+            z = Gc @ w
+            sig2 = float(w @ z)
+            if it == iters:
+                break
+            x = z
+        sig = max(sig2, 0.0) ** 0.5
+        sigma0 = sig if c == 0 else sigma0
+        keep = sig > tol * max(sigma0, 1e-30) and sig > 0
+        prev.append(x); prevw.append(w)
+        X.append(x * sig if keep else _torch.zeros_like(x))
+        Y.append(w / sig if keep else _torch.zeros_like(w))
+    X, Y = _torch.stack(X, 1), _torch.stack(Y, 1)
+    return (B @ X).float(), (C @ Y).float()
+
+
 def dad_reconstruct(delta, act, weight_grad, bias_grad=None, scale=1.0):
     """``weight_grad[out, in] = scale * delta @ act[:in].T`` and, when ``act`` has one extra row (the bias column of the
     augmented activations), ``bias_grad[out] = scale * delta @ act[in]`` - written straight into the gradient arena."""

@@ -330,3 +330,87 @@ def test_custom_example_model_is_nativizable():
     import torch
     net.eval()
     assert net(torch.randn(2, 1, 16, 16, 16)).shape == (2, 2)
+
+
+def test_coefficient_space_power_iteration_is_the_truncated_svd():
+    """The algorithm of csrc/lowrank.cu::lowrank_eig_kernel (PyTorch twin): top-k triplets of B C^T from the two n x n Gram
+    matrices only - reconstruction within 2 % of the optimal rank-k error, right factors orthonormal."""
+    import torch
+    from coinstac_dinunet_b200.ops.lowrank import lowrank_factor_reference
+    torch.manual_seed(0)
+    for rows_b, rows_c, n, rank in ((256, 67, 16, 10), (32, 33, 8, 10), (64, 300, 32, 4), (2, 33, 16, 10)):
+        decay = torch.logspace(0, -3, n)
+        B, C = torch.randn(rows_b, n) * decay, torch.randn(rows_c, n)
+        left, right = lowrank_factor_reference(B, C, rank, 40, 1e-6)
+        k = left.shape[1]
+        assert k == min(rank, rows_b, rows_c, n)
+        full = B.double() @ C.double().t()
+        U, S, Vh = torch.linalg.svd(full, full_matrices=False)
+        best = (U[:, :k] * S[:k]) @ Vh[:k]
+        err, opt = float((full - left.double() @ right.double().t()).norm()), float((full - best).norm())
+        assert err <= opt * 1.02 + 1e-6 * float(full.norm()), (rows_b, rows_c, n, err, opt)
+        gram = right.t() @ right
+        keep = gram.diagonal() > 0.5
+        assert torch.allclose(gram[keep][:, keep], torch.eye(int(keep.sum())), atol=5e-2)
+
+
+def test_powersgd_plan_tables_and_host_helpers():
+    """Descriptor tables of the batched PowerSGD kernels (built on the host, CPU is fine): every matrix gets disjoint P / Q
+    ranges, small or 1-D tensors are exchanged uncompressed, the gather / scatter segments are inverse to each other."""
+    import os
+    import numpy as np
+    import pytest
+    import torch
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'coinstac_dinunet_b200', 'ops', '_b200_ops.so')
+    if not os.path.exists(so):
+        pytest.skip('kernel library not built')
+    try:
+        from coinstac_dinunet_b200.ops.lowrank import PowerSGDPlan
+        params = [torch.nn.Parameter(torch.zeros(*s)) for s in ((256, 66), (256,), (128, 256), (2, 32), (64, 16, 3, 3, 3), (64,))]
+        offsets, off = [], 0
+        for p in params:
+            offsets.append(off); off += (p.numel() + 7) // 8 * 8
+        plan = PowerSGDPlan(params, offsets, 2, 'cpu')
+    except OSError as exc:
+        pytest.skip(f'cannot load the kernel library here: {exc}')
+    assert [m[:3] for m in plan.mats] == [(0, 256, 66), (2, 128, 256), (4, 64, 432)]          # (2, 32) has <= rank rows: dense
+    assert [l[0] for l in plan.low] == [1, 3, 5] and plan.low_numel == 256 + 64 + 64
+    assert plan.p_numel == 2 * (256 + 128 + 64) and plan.q_numel == 2 * (66 + 256 + 432)
+    desc = plan.desc.numpy().view([('g', '<i8'), ('p', '<i8'), ('q', '<i8'), ('n', '<i4'), ('m', '<i4')])
+    assert list(desc['g']) == [offsets[0], offsets[2], offsets[4]] and list(desc['p']) == [0, 512, 768]
+    g, s = plan.seg_gather.numpy().view('<i8').reshape(-1, 3), plan.seg_scatter.numpy().view('<i8').reshape(-1, 3)
+    assert np.array_equal(g[:, 0], s[:, 1]) and np.array_equal(g[:, 1], s[:, 0]) and np.array_equal(g[:, 2], s[:, 2])
+    assert g[0, 1] == plan.q_numel                        # rank-1 gradients ride behind the Q factors
+
+
+def test_lagged_readback_and_running_scores_on_cpu():
+    import torch
+    from coinstac_dinunet_b200.parallel.nvlink_learner import _LaggedReadback, _RunningScores
+    rb = _LaggedReadback(torch.device('cpu'), slots=4, lag=2)
+    for i in range(7):
+        rb.push(torch.tensor(float(i)))
+    assert rb.finish() == 6.0 and rb.count == 7
+    cache = {}
+    assert _LaggedReadback.for_site(cache, torch.device('cpu')) is _LaggedReadback.for_site(cache, torch.device('cpu'))
+
+    class T:
+        def new_averages(self):
+            from coinstac_dinunet_b200.metrics import COINNAverages
+            return COINNAverages(1)
+
+        def new_metrics(self):
+            from coinstac_dinunet_b200.metrics import Prf1a
+            return Prf1a()
+
+        def reduce_iteration(self, its):
+            return {k: v for k, v in its[0].items()}
+    t = T()
+    sc = _RunningScores(t)
+    for i in range(3):
+        a, m = t.new_averages(), t.new_metrics()
+        a.add(float(i), 4)
+        m.add(torch.tensor([1, 0, 1, 1]), torch.tensor([1, 0, 0, 1]))
+        sc.add([{'averages': a, 'metrics': m, 'loss': torch.tensor(float(i))}])
+    out = sc.result()
+    assert abs(out['averages'].get()[0] - 1.0) < 1e-6 and float(out['loss']) == 2.0
+    assert out['metrics'].get()[0] == 0.75                # accuracy over the 12 accumulated predictions
