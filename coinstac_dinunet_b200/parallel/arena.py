@@ -254,6 +254,15 @@ class DistArena:
         bufs = [b for b in (model.buffers() if model is not None else []) if b.is_floating_point()]
         ints = [b for b in (model.buffers() if model is not None else []) if not b.is_floating_point()]
         symmetric = self.backend == 'nvlink' and isinstance(self.param_buf, SymmetricBuffer)
+        if symmetric:
+            # every site must be able to alias the source's buffers, or nobody takes the peer-copy route
+            try:
+                ok = self.param_buf.peer_tensor(src).numel() == self.numel
+            except Exception:
+                ok = False
+            votes = _torch.tensor([int(ok)], dtype=_torch.int64, device=dev)
+            _dist.all_reduce(votes, op=_dist.ReduceOp.MIN, group=self.group)
+            symmetric = bool(int(votes.item()))
         staging = self.grad_buf if (symmetric and isinstance(self.grad_buf, SymmetricBuffer)) else None
 
         def sync():
