@@ -3,7 +3,7 @@
 // conv1 -> BatchNorm -> ReLU -> MaxPool(2) at 8 x 121x145x121 produces a 543 MB bf16 conv output that the unfused
 // pipeline writes once and reads three times (pool forward, BN backward, weight gradient) and a second 543 MB
 // gradient tensor that is written and read once: ~2.7 GB of HBM traffic and four bandwidth/instruction bound
-// kernels (~0.95 ms per step).  The banded-Toeplitz formulation of conv1_toeplitz.cu makes the convolution itself so
+// kernels (~0.95 ms per step).  The banded-Toeplitz formulation (the W axis of the volume is the GEMM K axis) makes the convolution so
 // cheap on the tensor cores (45 us of tcgen05 time per pass) that it is faster to RECOMPUTE it than to store it:
 //
 //   MODE_STATS  conv -> per-channel sum / sum of squares of the fp32 accumulators            (nothing else written)
