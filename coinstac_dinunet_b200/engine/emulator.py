@@ -19,25 +19,29 @@ from ..config.keys import Phase
 
 
 def _copy_tree_flat(src, dst):
-    """Copy every regular file of ``src`` into ``dst`` (created on demand)."""
-    if not _os.path.isdir(src):
+    """Copy every regular file of ``src`` into ``dst`` (created on demand).  An empty ``src`` - every round of the device
+    transports - costs one ``scandir`` and nothing else."""
+    try:
+        with _os.scandir(src) as it:
+            files = [e.name for e in it if e.is_file()]
+    except (FileNotFoundError, NotADirectoryError):
+        return 0
+    if not files:
         return 0
     _os.makedirs(dst, exist_ok=True)
-    moved = 0
-    for name in _os.listdir(src):
-        path = _os.path.join(src, name)
-        if _os.path.isfile(path):
-            _shutil.copy(path, _os.path.join(dst, name))
-            moved += 1
-    return moved
+    for name in files:
+        _shutil.copy(_os.path.join(src, name), _os.path.join(dst, name))
+    return len(files)
 
 
 def _clear_files(folder):
-    if _os.path.isdir(folder):
-        for name in _os.listdir(folder):
-            path = _os.path.join(folder, name)
-            if _os.path.isfile(path):
-                _os.remove(path)
+    try:
+        with _os.scandir(folder) as it:
+            files = [e.path for e in it if e.is_file()]
+    except (FileNotFoundError, NotADirectoryError):
+        return
+    for path in files:
+        _os.remove(path)
 
 
 def node_state(work_dir, node_id):
