@@ -414,3 +414,52 @@ def test_lagged_readback_and_running_scores_on_cpu():
     out = sc.result()
     assert abs(out['averages'].get()[0] - 1.0) < 1e-6 and float(out['loss']) == 2.0
     assert out['metrics'].get()[0] == 0.75                # accuracy over the 12 accumulated predictions
+
+
+def test_arena_bucket_layout_and_shard_ownership_math():
+    """Host-side bookkeeping of the fused data plane, exercised without a GPU on a bare DistArena object: buckets are formed
+    in backward order over whole parameters and tile the arena; the (rank, lo, hi) ownership ranges of two-shot / NVLS launch
+    units follow the kernel's ceil(nvec / S) vectors-per-rank rule and tile every sharded unit exactly once."""
+    import torch
+    from coinstac_dinunet_b200.parallel import arena as A
+    ar = object.__new__(A.DistArena)
+    sizes = [432, 16, 16, 13824, 32, 32, 55296, 64, 64, 2359296, 256, 16384, 64, 128, 2]
+    ar.params = [torch.nn.Parameter(torch.zeros(n)) for n in sizes]
+    ar.offsets, off = [], 0
+    for n in sizes:
+        ar.offsets.append(off); off += A._round_up(n, A._ALIGN)
+    ar.world, ar.rank, ar.backend, ar.variant, ar.device, ar.group = 8, 3, 'nvlink', 'auto', torch.device('cpu'), None
+    ar.numel = A._round_up(off, 4 * ar.world)
+
+    class _Buf:
+        multicast_ptr = 1
+    ar.wire_buf, ar.grad_buf, ar.param_buf = None, _Buf(), _Buf()
+    # --- bucket construction (the part of enable_overlap that needs no device)
+    cap = (1 << 20) // 4
+    buckets, stop, members = [], ar.numel, []
+    for i in range(len(ar.params) - 1, -1, -1):
+        members.append(i)
+        start = ar.offsets[i]
+        if stop - start >= cap or i == 0:
+            start = 0 if i == 0 else start
+            buckets.append({'offset': start, 'numel': stop - start, 'params': members})
+            stop, members = start, []
+    assert sum(b['numel'] for b in buckets) == ar.numel and buckets[-1]['offset'] == 0
+    assert all(b['offset'] % 4 == 0 and b['numel'] % 4 == 0 for b in buckets)
+    assert buckets[0]['params'][-1] == 9                       # the 9.4 MB FC1 weight closes the first (head) bucket
+    ar._overlap = {'buckets': buckets}
+    # --- ownership ranges
+    ranges = ar.owner_ranges()
+    for b in buckets:
+        variant = ar._pick_variant(b['numel'] * 4)
+        mine = sorted((lo, hi, q) for q, lo, hi in ranges if b['offset'] <= lo < b['offset'] + b['numel'])
+        if variant == 'one_shot':
+            assert not mine                                    # replicated update: nothing to gather
+            continue
+        assert variant == 'nvls'
+        assert mine[0][0] == b['offset'] and mine[-1][1] == b['offset'] + b['numel']
+        assert all(a[1] == c[0] for a, c in zip(mine, mine[1:]))         # contiguous, no overlap
+        shard = -(-(b['numel'] // 4) // ar.world) * 4
+        assert all(hi - lo <= shard for lo, hi, _ in mine) and [q for _, _, q in mine] == sorted(q for _, _, q in mine)
+    ar.world = 2                                               # at two sites NVLS brings nothing: two-shot
+    assert ar._pick_variant(16 << 20) == 'two_shot' and ar._pick_variant(1024) == 'one_shot'
