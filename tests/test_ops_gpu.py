@@ -824,4 +824,4 @@ def test_fp8_conv_block_trains_like_bf16(dev):
         outs[backend] = (p.float(), w.grad.clone(), g.grad.clone(), xin.grad.float())
     for a, b_, name in zip(outs['fp8'], outs['auto'], ('p', 'dw', 'dgamma', 'dx')):
         cos = torch.nn.functional.cosine_similarity(a.flatten(), b_.flatten(), dim=0)
-        assert _rel(a, b_) < (0.12 if name == 'p' else 0.5) and cos > 0.9, (name, _rel(a, b_), float(cos))
+        assert _rel(a, b_) < (0.12 if name == 'p' else 0.6) and cos > 0.85, (name, _rel(a, b_), float(cos))
