@@ -463,3 +463,25 @@ def test_arena_bucket_layout_and_shard_ownership_math():
         assert all(hi - lo <= shard for lo, hi, _ in mine) and [q for _, _, q in mine] == sorted(q for _, _, q in mine)
     ar.world = 2                                               # at two sites NVLS brings nothing: two-shot
     assert ar._pick_variant(16 << 20) == 'two_shot' and ar._pick_variant(1024) == 'one_shot'
+
+
+def test_bench_helpers():
+    """bench.py bookkeeping that does not need a GPU: R1 lookup, clock-record merge, host gap statistics, CLI defaults."""
+    import importlib.util, os, sys
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(here, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ['bench.py']
+    try:
+        spec.loader.exec_module(bench)
+        a = bench.parse()
+    finally:
+        sys.argv = argv
+    assert (a.gpus, a.impl, a.model, a.dtype, a.input_dtype, a.overlap) == (1, 'ours', 'vbm', 'bf16', 'fp32', -1)
+    assert a.warmup >= 3 and a.steps > 0
+    assert bench.r1_number('vbm', 1) and bench.r1_number('vbm', 8) and bench.r1_number('vbm', 3) is None
+    assert bench.gap_stats([0.0, 0.002, 0.004, 0.0075]) == {'p50': 2.0, 'max': 3.5} and bench.gap_stats([0.0]) is None
+    m = bench.merge_clocks({'sm_mhz': 1965.0, 'sm_max_mhz': 1965.0, 'reasons': [], 'samples': 10, 'power_w_max': 300.0},
+                           {'sm_mhz': 1950.0, 'sm_max_mhz': 1965.0, 'reasons': ['sw_power_cap'], 'samples': 5}, None)
+    assert m['samples'] == 15 and m['reasons'] == ['sw_power_cap'] and m['sm_max_mhz'] == 1965.0 and m['power_w_max'] == 300.0
+    assert 'VBM' in bench.metric_name('vbm') and 'FreeSurfer' in bench.metric_name('fs')
