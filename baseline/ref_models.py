@@ -3,7 +3,6 @@
 from coinstac_dinunet_b200.  The architectures are documented in DESIGN.md and mirrored by
 coinstac_dinunet_b200.models.{fsnet,vbmnet} (same layer order => same parameter order/shapes).
 """
-import torch
 from torch import nn
 
 

@@ -10,11 +10,9 @@ the reference does not import on this image - they patch the *en
 the reference: a no-op ``matplotlib`` stub (package not installed) and the ``np.float``/``np.int``
 aliases NumPy 2 removed.
 """
-import json
 import os
 import shutil
 import sys
-import time
 import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))

@@ -15,8 +15,6 @@ import os as _os
 import shutil as _shutil
 import time as _time
 
-from ..config.keys import Phase
-
 
 def _copy_tree_flat(src, dst):
     """Copy every regular file of ``src`` into ``dst`` (created on demand).  An empty ``src`` - every round of the device

@@ -5,7 +5,6 @@ Architecture (ours to define): 66 aseg volume features ->
 the step is latency-bound, which is what the CUDA-graph + one-shot fused reduce path is for.
 The plain-PyTorch twin used by the reference arm lives in ``baseline/ref_models.py``.
 """
-import torch as _torch
 from torch import nn as _nn
 
 from .common import ArrayFileDataset, ClassificationTrainer

@@ -3,8 +3,6 @@
 Each function names the kernel it launches (``csrc/*.cu``) and has a PyTorch oracle that the GPU
 tests compare against (``tests/test_ops_gpu.py``).
 """
-import ctypes as _C
-
 import torch as _torch
 
 __all__ = ['count_binary', 'count_confusion', 'orthogonalize_', 'softmax_nll', 'SoftmaxNLL']

@@ -5,8 +5,6 @@ reconstruct-into-grad) with no cuSOLVER call, no host sync and no ``torch.matmul
 Every function has a PyTorch oracle next to it (``*_reference``) that the GPU tests compare against and that runs
 on CPU sites.
 """
-import ctypes as _C
-
 import numpy as _np
 import torch as _torch
 
@@ -128,10 +126,6 @@ def powersgd_round_reference(grads, errors, qs, rank, world_mean, use_error=True
 
 
 # ============================================================================================== rankDAD
-def _seg_args(t, kseg, seg_stride):
-    return t.data_ptr(), int(seg_stride), int(kseg)
-
-
 def lowrank_factor(B, C, rank, iters, tol, b_seg=None, c_seg=None, scale=1.0, out_left=None, out_right=None):
     """Top-``rank`` triplets of ``B @ C.T`` (B: [rowsB, n], C: [rowsC, n]) -> (left * sigma [rowsB, k], right [rowsC, k]).
 

@@ -85,11 +85,6 @@ def conv_block_grad_finalize(dwt, acc, conv_w, gamma, beta, cin, cout, transpose
     notify_grad_written(conv_w, gamma, beta)         # direct mode: autograd never sees these gradients
 
 
-def conv1_fused_enabled():
-    """Kept for callers that used to branch on it: the fused first block is the only first-block implementation."""
-    return True
-
-
 def conv1_pad_input_hd(x):
     """[N,D,H,W] fp32/bf16 -> zero-padded bf16 row matrix [N*(H+2)*(D+2), Wq], d' fastest (conv1_fused.cu)."""
     N, D, H, W = x.shape

@@ -140,12 +140,6 @@ class DistArena:
             _torch.cuda.synchronize(self.device)
             self.param_buf.barrier()
 
-    def shadow_view(self, p):
-        """bf16 view of parameter ``p`` in the shadow arena (native modules read this)."""
-        i = next(k for k, q in enumerate(self.params) if q is p)
-        off = self.offsets[i]
-        return self.shadow_buf.local[off:off + p.numel()].view(p.shape)
-
     def rebind_grads(self):
         """Re-attach ``p.grad`` to the arena (after ``optimizer.zero_grad(set_to_none=True)``)."""
         for p, off in zip(self.params, self.offsets):

@@ -82,9 +82,3 @@ def save_arrays(file_path, arrays):
 
 def load_arrays(file_path):
     return _np.load(file_path, allow_pickle=True)
-
-
-def flatten_params(tensors, dtype=None):
-    """Concatenate tensors into one 1-D tensor (used by the flat arenas and NCCL baseline)."""
-    flat = _torch.cat([t.detach().reshape(-1) for t in tensors])
-    return flat.to(dtype) if dtype is not None else flat
