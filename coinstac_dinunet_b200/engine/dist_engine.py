@@ -151,6 +151,14 @@ class DistEngine:
         return box[0]
 
     def step(self, local_fn, remote_fn):
+        try:
+            return self._step(local_fn, remote_fn)
+        except BaseException:
+            if self._mailbox is not None:                                   # wake the ranks that wait for this one
+                self._mailbox.abort()
+            raise
+
+    def _step(self, local_fn, remote_fn):
         t0 = _time.time()
         out = local_fn(self.site, self.cache, self.input, self.state)['output']
         gathered = self._gather(_jsonish(out))                              # doubles as file barrier

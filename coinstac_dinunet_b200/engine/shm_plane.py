@@ -3,19 +3,44 @@
 Per engine round every site sends one small dict to the aggregator and gets one back.  Over ``torch.distributed`` object
 collectives that is four collectives (two size exchanges, two payloads) - about a millisecond at eight ranks, with every
 GPU idle, every round.  All ranks of a ``DistEngine`` on one box can see one POSIX shared-memory segment instead: each rank
-owns a slot ``[seq u64 | len u64 | payload]`` (one extra slot carries the aggregator's answer), a message is published by
-writing the payload, then the length, then bumping the sequence number, and consumed by polling the sequence number.  x86
-total store order makes payload-before-sequence visible in that order; the poll loop is a bounded busy wait.
+owns a slot ``[seq u64 | len u64 | pid u64 | abort u64 | payload]`` (one extra slot carries the aggregator's answer), a
+message is published by writing the payload, then the length, then bumping the sequence number, and consumed by polling
+the sequence number.  x86 total store order makes payload-before-sequence visible in that order; the poll loop is a
+bounded busy wait.
+
+Failure detection: a waiting rank does not rely on the timeout alone.  Every ~thousand polls it looks at the
+``abort`` word of every slot (set by ``ShmMailbox.abort`` when a node raised - ``DistEngine.step`` does that before it
+re-raises) and checks that the process it is waiting for still exists (``pid`` word, same PID namespace on one box); either
+condition raises ``PeerFailure`` within milliseconds instead of leaving the survivors spinning.
 """
+import os as _os
 import pickle as _pickle
 import struct as _struct
 import time as _time
 from multiprocessing import shared_memory as _shm
 
-_HDR = 16
+_HDR = 32
 
 
 _OVERSIZE = '__coinn_via_torch_distributed__'
+
+
+class PeerFailure(RuntimeError):
+    """Another rank of the engine raised or died while this one was waiting for its message."""
+
+
+def _alive(pid):
+    try:
+        _os.kill(pid, 0)
+    except ProcessLookupError:
+        return False
+    except PermissionError:
+        return True
+    try:                                               # a zombie (dead, not yet reaped by the launcher) still has a pid
+        with open(f'/proc/{pid}/stat') as fp:
+            return fp.read().rsplit(')', 1)[1].split()[0] != 'Z'
+    except Exception:
+        return True
 
 
 class ShmMailbox:
@@ -38,6 +63,7 @@ class ShmMailbox:
                 resource_tracker.unregister(self.mem._name, 'shared_memory')
             except Exception:
                 pass
+        _struct.pack_into('<Q', self.mem.buf, self.rank * self.slot + 16, _os.getpid())
         self.seq = 0           # messages this rank has posted
         self.answers = 0       # aggregator answers consumed / posted
 
@@ -69,10 +95,30 @@ class ShmMailbox:
                 t0 = t0 or now
                 if now - t0 > self.timeout:
                     raise TimeoutError(f'control plane: slot {slot} never reached message {seq}')
+                self._check_peers(slot, liveness=(spins >> 10) & 0x3f == 1)
                 if spins > 200000:
                     _time.sleep(0.0005)                              # long waits (a validation epoch) yield the core
         n = _struct.unpack_from('<Q', self.mem.buf, base + 8)[0]
         return _pickle.loads(bytes(self.mem.buf[base + _HDR:base + _HDR + n]))
+
+    def _check_peers(self, slot, liveness=True):
+        """Slow path of a wait on ``slot``: has anybody aborted, is the writer of that slot still there?"""
+        for r in range(self.world):
+            if _struct.unpack_from('<Q', self.mem.buf, r * self.slot + 24)[0]:
+                raise PeerFailure(f'control plane: rank {r} aborted the run')
+        if not liveness:
+            return
+        writer = 0 if slot == self.world else slot
+        pid = _struct.unpack_from('<Q', self.mem.buf, writer * self.slot + 16)[0]
+        if pid and pid != _os.getpid() and not _alive(pid):
+            raise PeerFailure(f'control plane: rank {writer} (pid {pid}) is gone')
+
+    def abort(self):
+        """Tell every waiting rank that this one is not going to post again."""
+        try:
+            _struct.pack_into('<Q', self.mem.buf, self.rank * self.slot + 24, 1)
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ round protocol
     def gather(self, obj):

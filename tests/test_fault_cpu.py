@@ -71,3 +71,49 @@ def test_fold_level_resume(fs_sites, tmp_path):
     assert [t['remote'] for t in eng2.trace].count('next_run') == 2      # only folds 1 and 2 were trained
     rows = open(os.path.join(eng2.remote_state['outputDirectory'], 'fsv', 'global_test_metrics.csv')).read().strip().split('\n')
     assert len(rows) == 2 and len(eng2.remote_cache['serializable_global_test_scores']) == 3
+
+
+_MAILBOX_PEER = """
+import os, sys
+from coinstac_dinunet_b200.engine.shm_plane import ShmMailbox
+mb = ShmMailbox(sys.argv[1], 1, 2, slot_bytes=4096, create=False)      # rank 1 of 2
+mb.gather({'round': 1})
+assert mb.broadcast() == 'ack'
+if sys.argv[2] == 'abort':                              # what DistEngine.step does when a node raises
+    mb.abort()
+    os._exit(0)
+os._exit(17)                                            # no abort word, no clean-up - like a segfault or an OOM kill
+"""
+
+
+@pytest.mark.parametrize('behaviour', ['abort', 'die', 'zombie'])
+def test_control_plane_mailbox_detects_a_failed_peer(behaviour):
+    """A rank waiting on the shared-memory control plane learns within a fraction of a second that the rank it waits for
+    raised (abort word) or vanished (pid check; a dead-but-unreaped process counts as gone) - not after the half-hour
+    timeout."""
+    import os
+    import subprocess
+    import sys
+    import time
+    from coinstac_dinunet_b200.engine.shm_plane import PeerFailure, ShmMailbox
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mb = ShmMailbox(None, 0, 2, slot_bytes=4096, create=True, timeout_s=60.0)
+    proc = None
+    try:
+        proc = subprocess.Popen([sys.executable, '-c', _MAILBOX_PEER, mb.name, behaviour], cwd=root)
+        assert mb.gather({'round': 1}) == [{'round': 1}, {'round': 1}]
+        mb.broadcast('ack')
+        if behaviour == 'zombie':                       # dead but not reaped by its launcher yet: /proc/<pid>/stat says Z
+            while open(f'/proc/{proc.pid}/stat').read().rsplit(')', 1)[1].split()[0] != 'Z':
+                time.sleep(0.01)
+        else:
+            proc.wait(30)                               # reaped: the pid is really gone
+        t0 = time.monotonic()
+        with pytest.raises(PeerFailure) as err:
+            mb.gather({'round': 2})                     # rank 1 never posts message 2
+        assert time.monotonic() - t0 < 5.0
+        assert ('aborted' if behaviour == 'abort' else 'is gone') in str(err.value)
+    finally:
+        if proc is not None:
+            proc.wait(30)
+        mb.close()
