@@ -242,8 +242,9 @@ class NvlinkLearner(COINNLearner):
 
 class NvlinkPowerSGDLearner(NvlinkLearner):
     """PowerSGD over the device collectives (P/Q factors all-reduced instead of shipped as files).
-    Math as in ``distrib.powersgd`` (rank-r, error feedback, warm start); the two reductions per
-    step are ``torch.distributed`` all-reduces of the small factor buffers."""
+    Math as in ``distrib.powersgd`` (rank-r, error feedback, warm start).  On GPUs a compressed step is
+    ``_compressed_step_device`` (batched kernels + in-kernel NVLink all-reduce of the factor buffers); the per-matrix
+    PyTorch form below it is the CPU / gloo path and the oracle of the device path."""
     _overlap_ok = False
 
     def __init__(self, **kw):
@@ -363,6 +364,7 @@ class NvlinkPowerSGDLearner(NvlinkLearner):
                 self._compressed_step()
             self.st.iter += 1
             scores.add(step_its)
+        self.arena.check_health()
         self.cache['cursor'] = 0
         out['mode'] = Mode.VALIDATION_WAITING
         return scores.result(), out
@@ -501,6 +503,7 @@ class NvlinkDADLearner(NvlinkLearner):
                 scores.add(step_its)
         finally:
             self.cache['local_iterations'] = saved
+        self.arena.check_health()
         self.cache['cursor'] = 0
         out['mode'] = Mode.VALIDATION_WAITING
         return scores.result(), out
