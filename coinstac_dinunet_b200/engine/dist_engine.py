@@ -137,6 +137,8 @@ class DistEngine:
             return None
 
     def _gather(self, obj):
+        if self.world == 1:                      # a collective of one still pickles, stages and synchronises: ~0.5 ms per round
+            return [obj]
         if self._mailbox is not None:
             return self._mailbox.gather(obj)
         gathered = [None] * self.world if self.rank == 0 else None
@@ -144,6 +146,8 @@ class DistEngine:
         return gathered
 
     def _broadcast(self, payload):
+        if self.world == 1:
+            return payload
         if self._mailbox is not None:
             return self._mailbox.broadcast(payload)
         box = [payload]
