@@ -485,3 +485,71 @@ def test_bench_helpers():
                            {'sm_mhz': 1950.0, 'sm_max_mhz': 1965.0, 'reasons': ['sw_power_cap'], 'samples': 5}, None)
     assert m['samples'] == 15 and m['reasons'] == ['sw_power_cap'] and m['sm_max_mhz'] == 1965.0 and m['power_w_max'] == 300.0
     assert 'VBM' in bench.metric_name('vbm') and 'FreeSurfer' in bench.metric_name('fs')
+
+
+class _TorchConvBlock:
+    """fp32 PyTorch stand-in for ``ops.vbm.ConvBnReluPoolFn`` (same calling convention, channels-last activations) so the
+    host-side algebra of ``ops.nativize._conv_stack`` - channel padding, conv-bias folding, running-statistics handling - can be
+    checked on CPU against the user's original modules."""
+
+    @staticmethod
+    def apply(h, w, g, b, rm, rv, eps, mom, training, backend, nbt=None):
+        F = torch.nn.functional
+        x = h.unsqueeze(1) if h.dim() == 4 else h.permute(0, 4, 1, 2, 3)
+        y = F.conv3d(x.float(), w.float(), padding=1)
+        rm2, rv2 = rm.clone(), rv.clone()                    # (autograd keeps the buffers it is given; the kernels do not)
+        y = F.batch_norm(y, rm2, rv2, g, b, training, mom, eps)
+        with torch.no_grad():
+            rm.copy_(rm2), rv.copy_(rv2)
+        if nbt is not None:
+            nbt += 1
+        return F.max_pool3d(F.relu(y), 2).permute(0, 2, 3, 4, 1).contiguous()
+
+
+@pytest.mark.parametrize('chans,bias', [((1, 16, 32), False), ((3, 20, 40, 50), True), ((16, 32, 24), True), ((5, 64), False)])
+def test_nativize_conv_stack_algebra_matches_the_original_modules(chans, bias, monkeypatch):
+    """Zero-padded channels stay exactly zero through BN(gamma 1, beta 0)+ReLU+pool, a conv bias in front of BatchNorm only
+    shifts the tracked mean, and the user's BatchNorm buffers end up identical to those of the unmodified module - in
+    training (outputs, input / weight / BN gradients, running stats, num_batches_tracked) and in eval mode."""
+    import copy
+    from torch import nn
+    import importlib
+    from coinstac_dinunet_b200.ops import vbm
+    nz = importlib.import_module('coinstac_dinunet_b200.ops.nativize')   # (the package re-exports the function under this name)
+    monkeypatch.setattr(vbm, 'ConvBnReluPoolFn', _TorchConvBlock)
+    torch.manual_seed(3)
+    layers = []
+    for ci, co in zip(chans, chans[1:]):
+        layers += [nn.Conv3d(ci, co, 3, padding=1, bias=bias), nn.BatchNorm3d(co), nn.ReLU(), nn.MaxPool3d(2)]
+    ref = nn.Sequential(*layers).double()
+    for m in ref:
+        if isinstance(m, nn.BatchNorm3d):
+            m.weight.data.uniform_(0.5, 1.5), m.bias.data.normal_(0, 0.2)
+            m.running_mean.normal_(0, 0.1), m.running_var.uniform_(0.5, 2.0)
+    ref = ref.float()
+    ours = copy.deepcopy(ref)
+    plan = nz._plan(list(ours.children()))
+    assert [st[0] for st in plan] == ['stack'] and len(plan[0][1]) == len(chans) - 1
+    side = 2 ** (len(chans) - 1) * 2
+    # bf16-representable inputs: _conv_stack hands the kernels bf16 activations, the comparison should see only the algebra
+    x = torch.randn(2, chans[0], side, side, side).bfloat16().float()
+
+    for training in (True, False):
+        ref.train(training), ours.train(training)
+        xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        yr = ref(xr)
+        # the stand-in keeps fp32 between blocks; the real kernels round to bf16 there, which is what the GPU tests bound
+        yo = nz._conv_stack(plan[0][1], xo if chans[0] != 1 else xo[:, 0], training)
+        assert yo.shape == yr.shape
+        assert torch.allclose(yo, yr, rtol=1e-4, atol=1e-4), float((yo - yr).abs().max())
+        if training:
+            (yr.square().mean()).backward()
+            (yo.square().mean()).backward()
+            for (n, pr), (_, po) in zip(ref.named_parameters(), ours.named_parameters()):
+                if n.endswith('.bias') and isinstance(dict(ref.named_modules())[n.rsplit('.', 1)[0]], nn.Conv3d):
+                    assert po.grad is None or float(po.grad.abs().max()) < 1e-4        # a bias before BN has zero gradient
+                    continue
+                scale = float(pr.grad.abs().max()) + 1e-12
+                assert float((po.grad - pr.grad).abs().max()) <= 1e-3 * scale + 1e-7, n
+        for (n, br), (_, bo) in zip(ref.named_buffers(), ours.named_buffers()):
+            assert torch.allclose(bo.float(), br.float(), rtol=1e-4, atol=1e-5), n
