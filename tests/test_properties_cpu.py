@@ -3,7 +3,7 @@ splits, shard ownership, metric additivity, the MX-FP8 quantisation rule, wire f
 import numpy as np
 import pytest
 import torch
-from hypothesis import given, settings, strategies as st
+from hypothesis import assume, given, settings, strategies as st
 
 from coinstac_dinunet_b200.data import COINNPaddedDataSampler
 from coinstac_dinunet_b200.data.datautils import create_k_fold_splits, create_ratio_split
@@ -216,3 +216,40 @@ def test_gradient_wire_files_round_trip(shapes, dtype, tmp_path_factory):
     assert len(back) == len(arrays)
     for a, b in zip(arrays, back):
         assert b.dtype == a.dtype and b.shape == a.shape and np.array_equal(a, b)
+
+
+@FAST
+@given(n=st.integers(2, 24), m=st.integers(2, 24), rank=st.integers(1, 4), seed=st.integers(0, 10 ** 6))
+def test_powersgd_round_invariants(n, m, rank, seed):
+    """The PyTorch twin of the batched PowerSGD kernels (``ops.lowrank.powersgd_round_reference``; the GPU tests compare the
+    kernels against it): approximation + new error == gradient + old error exactly, the approximation has rank <= r, a
+    full-rank budget reproduces the matrix, and with warm start on a fixed matrix the residual falls to the SVD truncation
+    error (subspace iteration) - ref powersgd/__init__.py:61-181."""
+    from coinstac_dinunet_b200.ops.lowrank import powersgd_round_reference
+    assume(rank < min(n, m))                             # PowerSGDPlan sends matrices with min(n, m) <= rank uncompressed
+    g = torch.Generator().manual_seed(seed)
+    G = torch.randn(n, m, generator=g, dtype=torch.float64)
+    E = torch.randn(n, m, generator=g, dtype=torch.float64) * 0.1
+    Q = torch.randn(m, rank, generator=g, dtype=torch.float64)
+    approx, errs, qs = powersgd_round_reference([G], [E], [Q.clone()], rank, lambda ts: None)
+    assert torch.allclose(approx[0] + errs[0], G + E, atol=1e-10)
+    assert int(torch.linalg.matrix_rank(approx[0], tol=1e-8)) <= rank
+    assert qs[0].shape == (m, rank)
+
+    full = min(n, m)
+    Qf = torch.randn(m, full, generator=g, dtype=torch.float64)
+    a_full, e_full, _ = powersgd_round_reference([G], [torch.zeros_like(G)], [Qf], full, lambda ts: None)
+    if n <= m and float(torch.linalg.cond(G @ Qf)) < 1e4:        # P spans R^n -> P P^T is the identity
+        assert float(e_full[0].abs().max()) < 1e-4 * float(G.abs().max())       # (Gram-Schmidt carries an epsilon of 1e-8)
+
+    sv = torch.linalg.svdvals(G)
+    best = float(sv[rank:].square().sum().sqrt())
+    q = Q.clone()
+    for _ in range(60):                                  # warm start: the averaged Q of one step seeds the next
+        a, _, qs = powersgd_round_reference([G], [torch.zeros_like(G)], [q], rank, lambda ts: None)
+        q = qs[0]
+    resid = float((G - a[0]).norm())
+    assert resid >= best - 1e-8
+    gap = float(sv[rank - 1] - sv[rank]) if rank < len(sv) else 1.0
+    if gap > 0.2 * float(sv[0]):                         # well separated spectrum: 60 sweeps converge
+        assert resid <= best * 1.001 + 1e-6
