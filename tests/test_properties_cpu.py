@@ -9,7 +9,7 @@ from coinstac_dinunet_b200.data import COINNPaddedDataSampler
 from coinstac_dinunet_b200.data.datautils import create_k_fold_splits, create_ratio_split
 from coinstac_dinunet_b200.metrics import COINNAverages, ConfusionMatrix, Prf1a
 
-FAST = settings(max_examples=60, deadline=None)
+FAST = settings(max_examples=60, deadline=None, derandomize=True, database=None)   # same examples every run
 
 
 class _Sized:
