@@ -54,7 +54,8 @@ class COINNLocal:
                  patience: int = None, num_folds: int = None, split_ratio=None,
                  pretrain_args: dict = None, dataloader_args: dict = None, verbose=False,
                  monitor_metric='f1', metric_direction='maximize', log_header='Loss|Accuracy,F1',
-                 agg_engine='dSGD', num_reducers=2, precision_bits=32, **kw):
+                 agg_engine='dSGD', num_reducers=2, precision_bits=32, checkpoint_epochs: int = 0,
+                 resume: bool = False, **kw):
         self.out = {}
         self.cache = cache
         self.input = _FrozenDict(input)
@@ -67,7 +68,8 @@ class COINNLocal:
             pretrained_path=pretrained_path, patience=patience if patience else epochs,
             split_ratio=split_ratio, num_folds=num_folds, verbose=verbose, monitor_metric=monitor_metric,
             metric_direction=metric_direction, log_header=log_header, agg_engine=agg_engine,
-            num_reducers=num_reducers, precision_bits=precision_bits)
+            num_reducers=num_reducers, precision_bits=precision_bits,
+            checkpoint_epochs=checkpoint_epochs, resume=resume)      # (ours) epoch-level resume points, see COINNRemote
         defaults.update(**kw)
         self._args = _FrozenDict(defaults)
         self._pretrain_args = pretrain_args if pretrain_args else {}
@@ -129,7 +131,26 @@ class COINNLocal:
         trainer.init_nn(init_model=True, init_optim=True, set_devices=True, init_weights=True)
         self.cache['best_nn_state'] = f"best.{self.cache['task_id']}-{ix}.pt"
         self.cache['latest_nn_state'] = f"latest.{self.cache['task_id']}-{ix}.pt"
-        return {'phase': Phase.COMPUTATION}
+        out = {'phase': Phase.COMPUTATION}
+        if self.cache.get('resume_epoch') is not None:           # the aggregator found a committed resume point
+            out['resumed_epoch'] = self._load_resume_point(trainer, int(self.cache['resume_epoch']))
+        return out
+
+    # ------------------------------------------------------- epoch-level resume points (see COINNRemote._request_resume_point)
+    def _resume_path(self, epoch, ext='pt'):
+        return _os.path.join(self.cache['log_dir'], f"resume.{self.cache['task_id']}-{self.cache['split_ix']}.e{int(epoch)}.{ext}")
+
+    def _load_resume_point(self, trainer, epoch):
+        path = self._resume_path(epoch)
+        if not _os.path.exists(path):
+            raise FileNotFoundError(f"{self.state['clientId']}: the aggregator resumes fold {self.cache['split_ix']} at epoch "
+                                    f"{epoch} but {path} does not exist (was the output directory replaced?)")
+        trainer.load_checkpoint(file_path=path)
+        with open(self._resume_path(epoch, 'json')) as fp:
+            meta = _json.load(fp)
+        self.cache['local_epoch'] = int(meta.get('local_epoch', 0))
+        self.cache['resume_committed'] = epoch
+        return epoch
 
     def _pretrain_local(self, trainer_cls, datahandle_cls, train_dataset, validation_dataset):
         """Optional single-site warm-up on the site holding the most data (chosen by the
@@ -239,6 +260,29 @@ class COINNLocal:
         self._sync_optimizer_state()
         rt.trainer.save_checkpoint(file_path=self.cache['log_dir'] + _sep + self.cache['best_nn_state'])
 
+    def _do_save_resume_point(self, rt):
+        """Phase 2 of a resume point: model + optimizer (+ the loader epoch) of this site at the end of ``epoch``.  Files of
+        points older than the last COMMITTED one are pruned; the committed one stays until its successor is committed."""
+        epoch = int(self.input['save_resume_point'])
+        self._sync_optimizer_state()
+        rt.trainer.save_checkpoint(file_path=self._resume_path(epoch))
+        with open(self._resume_path(epoch, 'json'), 'w') as fp:
+            _json.dump({'epoch': epoch, 'local_epoch': int(self.cache.get('local_epoch', 0))}, fp)
+        self.out['resume_point_saved'] = epoch
+        keep_from = self.cache.get('resume_committed')
+        prefix = f"resume.{self.cache['task_id']}-{self.cache['split_ix']}.e"
+        for name in _os.listdir(self.cache['log_dir']):
+            if name.startswith(prefix):
+                try:
+                    e = int(name[len(prefix):].split('.')[0])
+                except ValueError:
+                    continue
+                if keep_from is not None and e < int(keep_from):
+                    _os.remove(_os.path.join(self.cache['log_dir'], name))
+
+    def _note_resume_commit(self, rt):
+        self.cache['resume_committed'] = int(self.input['resume_point_committed'])
+
     def _do_update(self, rt):
         self.out.update(**rt.learner.step())
 
@@ -267,6 +311,8 @@ class COINNLocal:
 
     _COMPUTATION_RULES = (
         (lambda self, rt: bool(self.input.get('save_current_as_best')), '_do_save_best'),
+        (lambda self, rt: self.input.get('resume_point_committed') is not None, '_note_resume_commit'),
+        (lambda self, rt: self.input.get('save_resume_point') is not None, '_do_save_resume_point'),
         (lambda self, rt: bool(self.input.get('update')), '_do_update'),
         (lambda self, rt: any(m == Mode.TRAIN for m in rt.modes), '_do_train'),
         (lambda self, rt: bool(rt.modes) and all(m == Mode.VALIDATION for m in rt.modes), '_do_validate'),

@@ -77,6 +77,9 @@ class COINNRemote:
         if not self.cache.get(Key.ARGS_CACHED):
             first_site = next(iter(self.input.values()))
             self.cache.update(**first_site['shared_args'])
+            for k in ('resume', 'checkpoint_epochs'):            # (ours) aggregator-side switches: a constructor kwarg wins
+                if kw.get(k):
+                    self.cache[k] = kw[k]
             self.cache[Key.ARGS_CACHED] = True
 
     # ------------------------------------------------------------------- folds
@@ -94,9 +97,10 @@ class COINNRemote:
         return _os.path.join(self.state['outputDirectory'], str(self.cache['task_id']), 'resume.json')
 
     def _maybe_resume(self):
-        """Fold-level resume (the reference has none): with ``resume=True`` folds recorded as finished
-        by an earlier (crashed / stopped) run over the same output directory are skipped and their test scores are
-        carried into the final cross-fold aggregate."""
+        """Resume (the reference has none): with ``resume=True`` folds recorded as finished by an earlier
+        (crashed / stopped) run over the same output directory are skipped and their test scores are carried into the
+        final cross-fold aggregate; if that run had committed an epoch-level resume point for the fold it was in
+        (``checkpoint_epochs``, see ``_request_resume_point``), that fold continues from there instead of epoch 0."""
         path = self._resume_file()
         if not self.cache.get('resume') or not _os.path.exists(path):
             return
@@ -110,6 +114,46 @@ class COINNRemote:
             f['seed'] = self.cache['seed']
         self.cache[Key.GLOBAL_TEST_SERIALIZABLE] = list(done.get('global_test_serializable', []))
         self.cache['resumed_folds'] = sorted(finished)
+        self.cache['_resume_point'] = done.get('in_progress')
+
+    # Epoch-level resume points are a two-phase commit, because the sites' checkpoints and the aggregator's counters must
+    # describe the same epoch: (1) after a validation round the aggregator asks for a resume point (``save_resume_point =
+    # epoch``) and stashes its own state of that moment; (2) every site writes ``resume.<task>-<fold>.e<epoch>.pt`` and
+    # answers ``resume_point_saved = epoch``; (3) only when ALL sites answered does the aggregator record the point in
+    # ``resume.json`` and announce ``resume_point_committed`` (sites then prune older files).  A crash anywhere in between
+    # leaves the previous committed point - and the files it names - intact.
+    def _request_resume_point(self, next_mode):
+        every = int(self.cache.get('checkpoint_epochs') or 0)
+        if not every or next_mode != Mode.TRAIN:
+            return
+        validations = self.cache['epoch'] // max(int(self.cache['validation_epochs']), 1)
+        if validations % every:
+            return
+        self.out['save_resume_point'] = int(self.cache['epoch'])
+        self.cache['_pending_resume'] = {
+            'split_ix': self.cache['fold']['split_ix'], 'epoch': int(self.cache['epoch']),
+            'best_val_epoch': self.cache['best_val_epoch'], 'best_val_score': self.cache['best_val_score'],
+            'train_log': [list(r) for r in self.cache[Key.TRAIN_LOG]],
+            'validation_log': [list(r) for r in self.cache[Key.VALIDATION_LOG]]}
+
+    def _commit_resume_point(self, rt=None):
+        pend = self.cache.get('_pending_resume')
+        if not pend or not check(all, 'resume_point_saved', pend['epoch'], self.input):
+            return
+        path = self._resume_file()
+        _os.makedirs(_os.path.dirname(path), exist_ok=True)
+        rec = {'completed_folds': [], 'seed': self.cache.get('seed'),
+               'global_test_serializable': self.cache[Key.GLOBAL_TEST_SERIALIZABLE]}
+        if _os.path.exists(path):
+            with open(path) as fp:
+                rec.update(_json.load(fp))
+        rec['in_progress'] = pend
+        tmp = path + '.tmp'
+        with open(tmp, 'w') as fp:
+            _json.dump(rec, fp)
+        _os.replace(tmp, path)                       # atomic: a crash never leaves half a record
+        self.out['resume_point_committed'] = pend['epoch']
+        self.cache.pop('_pending_resume', None)
 
     def _record_fold_done(self):
         path = self._resume_file()
@@ -137,10 +181,21 @@ class COINNRemote:
         for k in (Key.TRAIN_LOG, Key.VALIDATION_LOG, Key.TEST_METRICS):
             self.cache[k] = []
 
+        self.cache.pop('_pending_resume', None)
+        point = self.cache.pop('_resume_point', None)
+        resume_epoch = None
+        if point and str(point.get('split_ix')) == fold['split_ix']:
+            resume_epoch = int(point['epoch'])
+            self.cache.update(epoch=resume_epoch, best_val_epoch=point['best_val_epoch'],
+                              best_val_score=point['best_val_score'], resumed_epoch=resume_epoch)
+            self.cache[Key.TRAIN_LOG] = [list(r) for r in point.get('train_log', [])]
+            self.cache[Key.VALIDATION_LOG] = [list(r) for r in point.get('validation_log', [])]
+
         train_sizes = {site: self.cache['data_size'][site][fold['split_ix']].get('train', 0)
                        for site in self.input}
         biggest = max(train_sizes, key=train_sizes.get)
-        return {site: {**fold, 'pretrain': site == biggest} for site in self.input}
+        return {site: {**fold, 'pretrain': site == biggest and resume_epoch is None, 'resume_epoch': resume_epoch}
+                for site in self.input}
 
     # ------------------------------------------------------------------ scores
     def _reduce_scores(self, trainer, entries):
@@ -238,7 +293,9 @@ class COINNRemote:
 
     def _on_all_train_waiting(self, rt):
         info = self._on_epoch_end(rt.reducer)
-        self.out['global_modes'] = self._set_mode(mode=self._next_epoch(**info)['mode'])
+        nxt = self._next_epoch(**info)['mode']
+        self.out['global_modes'] = self._set_mode(mode=nxt)
+        self._request_resume_point(nxt)
 
     def _on_all_next_run_waiting(self, rt):
         self._on_run_end(rt.trainer)
@@ -259,6 +316,7 @@ class COINNRemote:
         ('phase', Phase.INIT_RUNS, '_on_all_init'),
         ('phase', Phase.PRE_COMPUTATION, '_on_all_pre_computation'),
         (None, None, '_echo_modes'),                                   # unconditional: default mode echo
+        (None, None, '_commit_resume_point'),                          # unconditional: phase 3 of a resume point, if one is pending
         ('phase', Phase.COMPUTATION, '_on_all_computation'),
         ('phase', Phase.NEXT_RUN_WAITING, '_on_all_next_run_waiting'),
     )

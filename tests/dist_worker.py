@@ -24,8 +24,29 @@ def scenario_protocol(work, opts):
                 epochs=int(opts.get('epochs', 2)), reduce_variant=opts.get('reduce_variant', 'auto'),
                 overlap_backward=opts.get('overlap') == '1', bucket_bytes=int(opts.get('bucket_bytes', 64 << 10)),
                 precision_bits=int(opts.get('precision_bits', 32)), dad_reduction_rank=int(opts.get('dad_rank', 10)),
+                checkpoint_epochs=int(opts.get('checkpoint_epochs', 0)), resume=opts.get('resume') == '1',
                 gpus=[int(os.environ.get('LOCAL_RANK', 0))] if torch.cuda.is_available() else None)
     eng = DistEngine(work, inputspec=spec)
+    died = {}
+    if opts.get('die_at_epoch'):                        # power cut once the aggregator has committed that resume point
+        class PowerCut(Exception):
+            pass
+        orig_step = eng.step
+
+        def step(lf, rf):
+            ok = orig_step(lf, rf)
+            box = [None]
+            if eng.rank == 0:
+                path = os.path.join(eng.remote_state['outputDirectory'], 'fsv', 'resume.json')
+                if os.path.exists(path):
+                    with open(path) as fp:
+                        box[0] = (json.load(fp).get('in_progress') or {}).get('epoch')
+            dist.broadcast_object_list(box, src=0)
+            if box[0] is not None and box[0] >= int(opts['die_at_epoch']):
+                died['epoch'] = box[0]
+                raise PowerCut()
+            return ok
+        eng.step = step
     # count torch.distributed collectives issued INSIDE a compressed / rankDAD optimizer step (the device data plane
     # must not issue any: the exchange is in-kernel over symmetric memory)
     import coinstac_dinunet_b200.parallel.nvlink_learner as nvl
@@ -55,7 +76,15 @@ def scenario_protocol(work, opts):
     sizes = [24, 18, 30, 12, 20, 16, 28, 22]
     write_synthetic_site(eng.state['baseDirectory'], sizes[eng.rank % len(sizes)], (66,), seed=eng.rank)
     local_kw = {'pretrain_args': {'epochs': 2}} if opts.get('pretrain') == '1' else None
-    rounds = eng.run_nodes(FSVTrainer, FSVDataset, local_kw=local_kw, max_rounds=500)
+    try:
+        rounds = eng.run_nodes(FSVTrainer, FSVDataset, local_kw=local_kw, remote_kw={'seed': 7}, max_rounds=500)
+    except Exception:
+        if not died:
+            raise
+        if eng.rank == 0:
+            with open(os.path.join(work, 'result.json'), 'w') as fp:
+                json.dump({'died_at_epoch': died['epoch']}, fp)
+        return
     model = eng.cache['nn']['fs_net']
     flat = torch.cat([p.detach().float().reshape(-1).cpu() for p in model.parameters()])
     gathered = [None] * eng.world
@@ -67,7 +96,8 @@ def scenario_protocol(work, opts):
                'backend': eng.cache['_arena'].backend, 'fused_steps': eng.cache['_arena'].steps_done,
                'graphed': '_graph_step' in eng.cache, 'param_sum': float(gathered[0].double().sum()),
                'trace': [t['remote'] for t in eng.trace], 'weights_broadcast': eng.cache.get('_weights_broadcast'),
-               'collectives_in_steps': inside['calls'], 'compressed_steps': inside['steps']}
+               'collectives_in_steps': inside['calls'], 'compressed_steps': inside['steps'],
+               'resumed_epoch': eng.remote_cache.get('resumed_epoch'), 'train_log': eng.remote_cache.get('train_log')}
         with open(os.path.join(work, 'result.json'), 'w') as fp:
             json.dump(res, fp)
 

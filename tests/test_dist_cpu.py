@@ -47,3 +47,17 @@ def test_control_plane_mailbox_handles_oversized_messages(tmp_path):
     assert res['csv'] and res['trace'][-2] == 'success' and res['replicas_identical']
     res2 = run_workers('protocol', tmp_path / 'gloo', port=29616, extra=['agg_engine=dSGD'], env={'COINN_CTL_SHM': '0'})
     assert res2['trace'] == res['trace'] and res2['rounds'] == res['rounds']      # (the fold seed is drawn per run)
+
+
+def test_epoch_level_resume_over_the_device_transport(tmp_path):
+    """The resume points of ``checkpoint_epochs`` through DistEngine + NvlinkLearner (one engine round = one epoch of fused
+    steps): a 2-site run killed after the epoch-3 point was committed and restarted with ``resume=1`` ends with the weights
+    and the training log of the undisturbed run."""
+    common = ['agg_engine=dSGD', 'epochs=5', 'checkpoint_epochs=1']
+    clean = run_workers('protocol', tmp_path / 'clean', port=29617, extra=common)
+    cut = run_workers('protocol', tmp_path / 'cut', port=29618, extra=common + ['die_at_epoch=3'])
+    assert cut == {'died_at_epoch': 3}
+    res = run_workers('protocol', tmp_path / 'cut', port=29619, extra=common + ['resume=1'])
+    assert res['resumed_epoch'] == 3 and res['trace'][-2] == 'success' and res['replicas_identical']
+    assert res['param_sum'] == clean['param_sum'] and res['train_log'] == clean['train_log']
+    assert clean['resumed_epoch'] is None

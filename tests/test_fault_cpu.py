@@ -117,3 +117,50 @@ def test_control_plane_mailbox_detects_a_failed_peer(behaviour):
         if proc is not None:
             proc.wait(30)
         mb.close()
+
+
+def test_epoch_level_resume_continues_a_fold_bit_exactly(fs_sites):
+    """``checkpoint_epochs=1``: after every validation round the aggregator requests a resume point, the sites write
+    ``resume.<task>-<fold>.e<epoch>.pt`` and the point is committed once all of them answered.  A run killed in the middle of
+    a fold and restarted with empty caches and ``resume=True`` picks the fold up at the committed epoch and finishes with
+    exactly the weights, logs and scores of an undisturbed run."""
+    import json
+    import os
+    from coinstac_dinunet_b200.engine import InProcessEngine
+    spec = {'num_folds': None, 'split_ratio': [0.6, 0.2, 0.2], 'epochs': 5, 'checkpoint_epochs': 1}
+    clean = fs_sites(spec=spec)
+    clean.run_nodes(FSVTrainer, FSVDataset, max_rounds=5000)
+    want = _flat(clean.site_cache['local0'])
+    want_log = clean.remote_cache['train_log']
+
+    import shutil
+    shutil.rmtree(clean.work_dir)
+    eng = fs_sites(spec=spec)
+    seen = []
+
+    def power_cut(rnd, site):
+        path = os.path.join(eng.remote_state['outputDirectory'], 'fsv', 'resume.json')
+        if os.path.exists(path):
+            with open(path) as fp:
+                point = json.load(fp).get('in_progress')
+            if point and point['epoch'] >= 3:
+                seen.append(point['epoch'])
+                raise KeyboardInterrupt('power cut')
+    eng.fault_hook = power_cut
+    with pytest.raises(KeyboardInterrupt):
+        eng.run_nodes(FSVTrainer, FSVDataset, max_rounds=5000)
+    assert seen == [3]
+    log_dir = os.path.join(eng.site_state['local0']['outputDirectory'], 'fsv', 'fold_0')
+    kept = sorted(n for n in os.listdir(log_dir) if n.startswith('resume.'))
+    assert 'resume.fsv-0.e3.pt' in kept and 'resume.fsv-0.e1.pt' not in kept       # older points are pruned
+
+    base = dict(task_id='fsv', mode='train', data_dir='data', labels_file='labels.json', input_size=66, num_class=2,
+                batch_size=4, learning_rate=1e-2, seed=7, monitor_metric='f1', metric_direction='maximize',
+                log_header='Loss|Accuracy,F1', verbose=False, resume=True, **spec)
+    eng2 = InProcessEngine(eng.work_dir, n_sites=2, inputspec=base)                 # same directories, empty caches
+    eng2.run_nodes(FSVTrainer, FSVDataset, max_rounds=5000)
+    assert eng2.remote_cache['resumed_epoch'] == 3
+    assert eng2.trace[-2]['remote'] == 'success'
+    assert torch.equal(_flat(eng2.site_cache['local0']), want), 'a resumed fold must end where the undisturbed run ends'
+    assert torch.equal(_flat(eng2.site_cache['local0']), _flat(eng2.site_cache['local1']))
+    assert eng2.remote_cache['train_log'] == want_log
