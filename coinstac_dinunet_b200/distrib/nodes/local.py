@@ -149,6 +149,10 @@ class COINNLocal:
         with open(self._resume_path(epoch, 'json')) as fp:
             meta = _json.load(fp)
         self.cache['local_epoch'] = int(meta.get('local_epoch', 0))
+        extra = self._resume_path(epoch, 'engine.pt')
+        if _os.path.exists(extra):                               # engine state that lives outside model / optimizer
+            import torch as _torch
+            self.cache.update(_torch.load(extra, weights_only=False))
         self.cache['resume_committed'] = epoch
         return epoch
 
@@ -268,6 +272,10 @@ class COINNLocal:
         rt.trainer.save_checkpoint(file_path=self._resume_path(epoch))
         with open(self._resume_path(epoch, 'json'), 'w') as fp:
             _json.dump({'epoch': epoch, 'local_epoch': int(self.cache.get('local_epoch', 0))}, fp)
+        engine_state = {k: self.cache[k] for k in ('powerSGD_state',) if k in self.cache}
+        if engine_state:                                         # PowerSGD: error feedback, warm-start factors, iteration count
+            import torch as _torch
+            _torch.save(engine_state, self._resume_path(epoch, 'engine.pt'))
         self.out['resume_point_saved'] = epoch
         keep_from = self.cache.get('resume_committed')
         prefix = f"resume.{self.cache['task_id']}-{self.cache['split_ix']}.e"

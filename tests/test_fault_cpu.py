@@ -119,15 +119,18 @@ def test_control_plane_mailbox_detects_a_failed_peer(behaviour):
         mb.close()
 
 
-def test_epoch_level_resume_continues_a_fold_bit_exactly(fs_sites):
+@pytest.mark.parametrize('engine', ['dSGD', 'powerSGD'])
+def test_epoch_level_resume_continues_a_fold_bit_exactly(fs_sites, engine):
     """``checkpoint_epochs=1``: after every validation round the aggregator requests a resume point, the sites write
     ``resume.<task>-<fold>.e<epoch>.pt`` and the point is committed once all of them answered.  A run killed in the middle of
     a fold and restarted with empty caches and ``resume=True`` picks the fold up at the committed epoch and finishes with
-    exactly the weights, logs and scores of an undisturbed run."""
+    exactly the weights, logs and scores of an undisturbed run.  With PowerSGD the point also carries the engine state
+    (error feedback, warm-start factors, iteration count)."""
     import json
     import os
     from coinstac_dinunet_b200.engine import InProcessEngine
-    spec = {'num_folds': None, 'split_ratio': [0.6, 0.2, 0.2], 'epochs': 5, 'checkpoint_epochs': 1}
+    spec = {'num_folds': None, 'split_ratio': [0.6, 0.2, 0.2], 'epochs': 5, 'checkpoint_epochs': 1, 'agg_engine': engine,
+            'start_powerSGD_iter': 2, 'matrix_approximation_rank': 2}
     clean = fs_sites(spec=spec)
     clean.run_nodes(FSVTrainer, FSVDataset, max_rounds=5000)
     want = _flat(clean.site_cache['local0'])
