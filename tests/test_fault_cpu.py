@@ -119,7 +119,7 @@ def test_control_plane_mailbox_detects_a_failed_peer(behaviour):
         mb.close()
 
 
-@pytest.mark.parametrize('engine', ['dSGD', 'powerSGD'])
+@pytest.mark.parametrize('engine', ['dSGD', 'powerSGD', 'rankDAD'])
 def test_epoch_level_resume_continues_a_fold_bit_exactly(fs_sites, engine):
     """``checkpoint_epochs=1``: after every validation round the aggregator requests a resume point, the sites write
     ``resume.<task>-<fold>.e<epoch>.pt`` and the point is committed once all of them answered.  A run killed in the middle of
