@@ -138,3 +138,83 @@ def test_multiclass_protocol_uses_confusion_matrix(tmp_path):
     path = os.path.join(eng.remote_state['outputDirectory'], 'fsv', 'global_test_metrics.csv')
     rows = list(csv.reader(open(path)))
     assert len(rows) >= 2 and all(0.0 <= float(v) <= 1.0 for v in rows[-1][1:] if v not in ('', 'nan'))
+
+
+def test_user_defined_metric_travels_through_the_protocol(fs_sites):
+    """README highlight 5 of the reference: a ``COINNMetrics`` subclass written by the user (here: a Brier score, lower is
+    better) is created through ``new_metrics``, serialised by the sites, reduced by the aggregator and drives model selection
+    (``monitor_metric='brier'``, ``metric_direction='minimize'``) - ref metrics.py:17-84, remote.py:105-141, 281-284."""
+    from coinstac_dinunet_b200.metrics import COINNMetrics
+
+    class Brier(COINNMetrics):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            self.sq, self.n, self._reduced = 0.0, 0, None
+
+        def add(self, prob, true):
+            self.sq += float(((prob.detach().float() - true.float()) ** 2).sum())
+            self.n += int(true.numel())
+
+        def accumulate(self, other):
+            self.sq, self.n = self.sq + other.sq, self.n + other.n
+
+        def reset(self):
+            self.sq, self.n = 0.0, 0
+
+        @property
+        def brier(self):
+            return self._reduced if self._reduced is not None else self.sq / max(self.n, 1)
+
+        def get(self):
+            return [round(self.brier, 5)]
+
+        def serialize(self, **kw):
+            return [self.sq, self.n]
+
+        def reduce_sites(self, scores):
+            tot = np.asarray(scores, dtype=np.float64).sum(0) if len(scores) else np.zeros(2)
+            self._reduced = float(tot[0] / max(tot[1], 1))
+
+    class BrierTrainer(FSVTrainer):
+        def new_metrics(self):
+            return Brier()
+
+        def iteration(self, batch):
+            x, y = self._inputs(batch)
+            logits = self.nn['fs_net'](x)
+            loss = torch.nn.functional.cross_entropy(logits, y)
+            avg, met = self.new_averages(), self.new_metrics()
+            avg.add(loss.detach(), len(y))
+            met.add(torch.softmax(logits, 1)[:, 1], y)
+            return {'loss': loss, 'averages': avg, 'metrics': met}
+
+    eng = fs_sites(spec={'num_folds': None, 'split_ratio': [0.6, 0.2, 0.2], 'epochs': 4, 'monitor_metric': 'brier',
+                         'metric_direction': 'minimize', 'log_header': 'Loss|Brier'})
+    eng.run_nodes(BrierTrainer, FSVDataset, max_rounds=3000)
+    rc = eng.remote_cache
+    assert eng.trace[-2]['remote'] == 'success'
+    val = [row[1] for row in rc['validation_log']]
+    assert len(val) >= 4 and all(0.0 <= v <= 1.0 for v in val)
+    assert rc['best_val_score'] == pytest.approx(min(val), abs=2e-4)         # minimised (improvements below score_delta do not count)
+    train = [row[1] for row in rc['train_log']]
+    assert train[-1] < train[0] and train[0] > 0.01                           # and it learns
+    assert len(rc['test_metrics'][0]) == 2                                    # [loss, brier]
+    out_dir = os.path.join(eng.remote_state['outputDirectory'], 'fsv')
+    assert os.path.exists(os.path.join(out_dir, 'global_test_metrics.csv'))
+
+
+def test_profile_flag_reports_per_site_phase_timings(tmp_path):
+    """README highlight 7 of the reference ("realtime profiling each site by specifying in compspec"): ``profile: true`` makes
+    every site time its forward/backward and reduce/update phases and ship the table with its output."""
+    from coinstac_dinunet_b200.engine import InProcessEngine
+    spec = dict(task_id='fsv', mode='train', data_dir='data', labels_file='labels.json', input_size=66, num_class=2,
+                batch_size=4, epochs=1, num_folds=None, split_ratio=[0.6, 0.2, 0.2], learning_rate=1e-2, seed=7,
+                transport='nvlink', profile=True, verbose=False)
+    eng = InProcessEngine(tmp_path / 'work', n_sites=1, inputspec=spec)
+    write_synthetic_site(eng.site_state['local0']['baseDirectory'], 24, (66,), seed=0)
+    eng.run_nodes(FSVTrainer, FSVDataset, max_rounds=500)
+    log = eng.site_cache['local0'].get('profile_log')
+    assert log, 'no profile table in the site cache'
+    last = log[-1] if isinstance(log, list) else log
+    text = json.dumps(last, default=str)
+    assert 'forward_backward' in text and 'reduce_update' in text
