@@ -218,3 +218,64 @@ def test_profile_flag_reports_per_site_phase_timings(tmp_path):
     last = log[-1] if isinstance(log, list) else log
     text = json.dumps(last, default=str)
     assert 'forward_backward' in text and 'reduce_update' in text
+
+
+def test_multi_network_training_scheme_with_a_custom_learner(fs_sites):
+    """README highlights 1 + 6 of the reference: a trainer that owns TWO networks with their own optimizers (encoder + head),
+    and a user learner that puts both on the wire.  With the stock learner only the first network is exchanged (the
+    reference's rule, learner.py:30-37); with the custom one every replica of both networks stays identical, and the
+    checkpoint keeps both models and both optimizers (the reference drops all but the last)."""
+    from torch import nn
+
+    class TwoNetTrainer(FSVTrainer):
+        def _init_nn_model(self):
+            self.nn['encoder'] = nn.Sequential(nn.Linear(66, 16), nn.ReLU())
+            self.nn['head'] = nn.Linear(16, 2)
+
+        def _init_optimizer(self):
+            self.optimizer['enc_opt'] = torch.optim.Adam(self.nn['encoder'].parameters(), lr=1e-2)
+            self.optimizer['head_opt'] = torch.optim.SGD(self.nn['head'].parameters(), lr=5e-2)
+
+        def iteration(self, batch):
+            x, y = self._inputs(batch)
+            logits = self.nn['head'](self.nn['encoder'](x))
+            loss = torch.nn.functional.cross_entropy(logits, y)
+            avg, met = self.new_averages(), self.new_metrics()
+            avg.add(loss.detach(), len(y))
+            met.add(logits.argmax(1), y)
+            return {'loss': loss, 'averages': avg, 'metrics': met}
+
+    class AllNetsLearner(COINNLearner):
+        @property
+        def model(self):                                   # every network, in the trainer's order, as one parameter list
+            return nn.ModuleList(list(self.trainer.nn.values()))
+
+        def backward(self):
+            for opt in self.trainer.optimizer.values():
+                opt.zero_grad()
+            return super().backward()
+
+        def step(self):
+            out = super().step()                           # installs the averaged gradients, steps the first optimizer
+            for opt in list(self.trainer.optimizer.values())[1:]:
+                opt.step()
+            return out
+
+    def flat(cache, name):
+        return torch.cat([p.detach().reshape(-1) for p in cache['nn'][name].parameters()])
+
+    spec = {'num_folds': None, 'split_ratio': [0.6, 0.2, 0.2], 'epochs': 2, 'agg_engine': 'custom'}
+    eng = fs_sites(spec=spec)
+    eng.run_nodes(TwoNetTrainer, FSVDataset, learner_cls=AllNetsLearner, max_rounds=2000)
+    assert eng.trace[-2]['remote'] == 'success'
+    a, b = eng.site_cache['local0'], eng.site_cache['local1']
+    assert torch.equal(flat(a, 'encoder'), flat(b, 'encoder')) and torch.equal(flat(a, 'head'), flat(b, 'head'))
+    chk = torch.load(os.path.join(a['log_dir'], a['latest_nn_state']), weights_only=False)
+    assert set(chk['models']) == {'encoder', 'head'} and set(chk['optimizers']) == {'enc_opt', 'head_opt'}
+
+    import shutil
+    shutil.rmtree(eng.work_dir)
+    eng = fs_sites(spec=spec)                              # stock learner: only the first network is distributed
+    eng.run_nodes(TwoNetTrainer, FSVDataset, max_rounds=2000)
+    a, b = eng.site_cache['local0'], eng.site_cache['local1']
+    assert eng.trace[-2]['remote'] == 'success' and torch.equal(flat(a, 'encoder'), flat(b, 'encoder'))
