@@ -279,3 +279,29 @@ def test_multi_network_training_scheme_with_a_custom_learner(fs_sites):
     eng.run_nodes(TwoNetTrainer, FSVDataset, max_rounds=2000)
     a, b = eng.site_cache['local0'], eng.site_cache['local1']
     assert eng.trace[-2]['remote'] == 'success' and torch.equal(flat(a, 'encoder'), flat(b, 'encoder'))
+
+
+def test_custom_data_handle_filters_the_site_listing(fs_sites):
+    """"Define custom DataHandle" (reference README, advanced use cases): a user ``COINNDataHandle`` that hides some of a site's
+    files from the split (``list_files``) and tweaks the loader arguments is used by the site nodes for everything -
+    splitting, training loaders and evaluation."""
+    seen = {'listed': 0, 'loaders': 0}
+
+    class EvenSubjectsOnly(COINNDataHandle):
+        def list_files(self):
+            files = [f for f in super().list_files() if int(f.split('_')[-1].split('.')[0]) % 2 == 0]
+            seen['listed'] = len(files)
+            return files
+
+        def get_loader(self, handle_key='', **kw):
+            seen['loaders'] += 1
+            return super().get_loader(handle_key=handle_key, **kw)
+
+    eng = fs_sites(spec={'num_folds': None, 'split_ratio': [0.6, 0.2, 0.2], 'epochs': 1}, sizes=(24, 24))
+    eng.run_nodes(FSVTrainer, FSVDataset, datahandle_cls=EvenSubjectsOnly, max_rounds=2000)
+    assert eng.trace[-2]['remote'] == 'success' and seen['listed'] == 12 and seen['loaders'] > 0
+    split_dir = eng.site_cache['local0']['split_dir']
+    with open(os.path.join(split_dir, os.listdir(split_dir)[0])) as fp:
+        split = json.load(fp)
+    names = split['train'] + split['validation'] + split['test']
+    assert len(names) == 12 and all(int(n.split('_')[-1].split('.')[0]) % 2 == 0 for n in names)
