@@ -553,3 +553,41 @@ def test_nativize_conv_stack_algebra_matches_the_original_modules(chans, bias, m
                 assert float((po.grad - pr.grad).abs().max()) <= 1e-3 * scale + 1e-7, n
         for (n, br), (_, bo) in zip(ref.named_buffers(), ours.named_buffers()):
             assert torch.allclose(bo.float(), br.float(), rtol=1e-4, atol=1e-5), n
+
+
+class _FlakyDataset:
+    """Module-level (picklable for worker processes): every third sample 'fails to load' (returns None); the others carry a
+    NumPy random number so worker seeding is observable."""
+
+    def __init__(self, n=12):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, ix):
+        import numpy as _np
+        if ix % 3 == 2:
+            return None
+        return {'ix': torch.tensor(ix), 'noise': torch.tensor(float(_np.random.rand()))}
+
+
+def test_safe_collate_drops_failed_samples_and_workers_are_seeded():
+    """``safe_collate`` silently drops samples that failed to load (ref data.py:23-27); with ``seed_all`` every worker process
+    seeds NumPy from torch's per-worker seed, so augmentation noise is reproducible for a fixed base seed and differs between
+    workers (ref data.py:96-99)."""
+    from coinstac_dinunet_b200.data import COINNDataHandle, safe_collate
+    batch = safe_collate([{'x': torch.ones(2)}, None, {'x': torch.zeros(2)}, {}])
+    assert batch['x'].shape == (2, 2)
+
+    def run(seed):
+        dh = COINNDataHandle(cache={'seed_all': True, 'num_workers': 2, 'batch_size': 3, 'seed': 5}, input={}, state={})
+        torch.manual_seed(seed)
+        loader = dh.get_loader('train', dataset=_FlakyDataset(), shuffle=False)
+        assert loader.worker_init_fn is not None and loader.num_workers == 2
+        rows = [(b['ix'].tolist(), b['noise'].tolist()) for b in loader]
+        return rows
+    a, b, c = run(11), run(11), run(12)
+    assert [ix for ix, _ in a] == [[0, 1], [3, 4], [6, 7], [9, 10]]          # index 2, 5, 8, 11 were dropped, no crash
+    assert a == b and [n for _, n in a] != [n for _, n in c]                  # reproducible per base seed
+    assert a[0][1] != a[1][1]                                                 # worker 0 and worker 1 draw different streams
