@@ -236,7 +236,9 @@ class Prf1a(COINNMetrics):
 
     # --- scores ----------------------------------------------------------------
     def _r(self, x):
-        return round(float(x), self.num_precision)
+        # NOT round(float(x)): after reduce_sites the reduced score is a NumPy scalar and the reference rounds it with
+        # NumPy's rule (metrics.py:183-195) - the two rules differ on half-way cases such as 0.484105 -> 0.4841 / 0.48411
+        return round(x, self.num_precision)
 
     @property
     def precision(self):
@@ -275,8 +277,7 @@ class Prf1a(COINNMetrics):
         """Unweighted mean of per-site ``[accuracy, precision, recall]`` (ref metrics.py:217-218)."""
         if len(scores) == 0:
             return
-        acc, prec, rec = _np.asarray(scores, dtype=_np.float64).mean(0)
-        self._accuracy, self._precision, self._recall = float(acc), float(prec), float(rec)
+        self._accuracy, self._precision, self._recall = _np.asarray(scores, dtype=_np.float64).mean(0)
 
 
 class ConfusionMatrix(COINNMetrics):

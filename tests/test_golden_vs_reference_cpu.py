@@ -163,3 +163,191 @@ def test_same_job_same_curves_same_artefacts(tmp_path):
     o_csv = _rows(os.path.join(our_eng.remote_state['outputDirectory'], 'fsv', 'global_test_metrics.csv'))
     assert r_csv[0] == o_csv[0]
     assert np.allclose([float(v) for v in r_csv[1]], [float(v) for v in o_csv[1]], atol=2e-4)
+
+
+def test_vision_helpers_match_the_reference_on_random_inputs(tmp_path):
+    """Every pure helper of ``vision/imageutils.py`` ('Image + 15 helpers') against the reference's own function
+    on the same random inputs, plus the ``Image`` container (load / mask / ground truth / CLAHE / copy) on PNG files."""
+    _reference_or_skip()
+    try:
+        import coinstac_dinunet.vision.imageutils as ref
+    except Exception as exc:  # noqa: BLE001   (cv2 / PIL missing on this machine)
+        pytest.skip(f'reference imageutils not importable: {exc}')
+    from coinstac_dinunet_b200.vision import imageutils as ours
+    rng = np.random.default_rng(5)
+
+    def same(a, b):
+        if isinstance(a, dict):
+            assert a.keys() == b.keys()
+            for k in a:
+                same(a[k], b[k])
+        elif isinstance(a, (list, tuple)) and not isinstance(a, np.ndarray):
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                same(x, y)
+        else:
+            a, b = np.asarray(a), np.asarray(b)
+            assert a.shape == b.shape and np.allclose(a.astype(np.float64), b.astype(np.float64), atol=1e-6), (a, b)
+
+    seg = (rng.random((24, 31)) > 0.6).astype(np.uint8) * 255
+    truth = (rng.random((24, 31)) > 0.5).astype(np.uint8) * 255
+    grey = (rng.random((24, 31)) * 255).astype(np.uint8)
+    same(ours.get_rgb_scores(seg.copy(), truth.copy()), ref.get_rgb_scores(seg.copy(), truth.copy()))
+    same(ours.get_praf1(seg.copy(), truth.copy()), ref.get_praf1(seg.copy(), truth.copy()))
+    same(ours.rescale2d(grey.astype(np.float64)), ref.rescale2d(grey.astype(np.float64)))
+    vol = rng.random((3, 8, 9))
+    same(ours.rescale3d(vol.copy()), ref.rescale3d(vol.copy()))
+    same(ours.get_signed_diff_int8(seg.copy(), truth.copy()), ref.get_signed_diff_int8(seg.copy(), truth.copy()))
+    same(ours.whiten_image2d(grey.copy()), ref.whiten_image2d(grey.copy()))
+    for shape, chunk, off in (((24, 31), (8, 8), (5, 6)), ((20, 20), (7, 5), (7, 5)), ((9, 40), (9, 16), (3, 11))):
+        same(list(ours.get_chunk_indexes(shape, chunk, off)), list(ref.get_chunk_indexes(shape, chunk, off)))
+        pts = [(0, 0), (shape[0] - 1, shape[1] - 1), (shape[0] // 2, shape[1] // 3)]
+        same(ours.get_chunk_indices_by_index(shape, chunk, pts), ref.get_chunk_indices_by_index(shape, chunk, pts))
+        idx = list(ref.get_chunk_indexes(shape, chunk, off))
+        patches = rng.integers(0, 255, (len(idx), *chunk)).astype(np.uint8)
+        same(ours.merge_patches(patches.copy(), shape, chunk, off), ref.merge_patches(patches.copy(), shape, chunk, off))
+        for box in idx[:3] + idx[-2:]:
+            same(ours.expand_and_mirror_patch(shape, list(box), (6, 4)), ref.expand_and_mirror_patch(shape, list(box), (6, 4)))
+    blobs = np.zeros((30, 30), np.uint8)
+    blobs[2:5, 2:6] = 255
+    blobs[10:22, 8:25] = 255
+    blobs[26:28, 26:29] = 255
+    want = np.zeros((30, 30), bool)
+    want[10:22, 8:25] = True
+    try:
+        same(ours.largest_cc(blobs.copy()), ref.largest_cc(blobs.copy()))
+    except ModuleNotFoundError:                              # the reference needs scikit-image for this one
+        same(ours.largest_cc(blobs.copy()), want)
+    try:
+        kept = ref.remove_connected_comp(blobs.copy(), 10)
+    except (ModuleNotFoundError, ImportError, AttributeError):   # scipy.ndimage.measurements is gone in recent SciPy
+        kept = None
+    if kept is not None:
+        same(ours.remove_connected_comp(blobs.copy(), 10), kept)
+    same(ours.map_img_to_img2d(truth.copy(), grey.copy()), ref.map_img_to_img2d(truth.copy(), grey.copy()))
+    for i, j, eight in ((3, 4, False), (0, 0, True), (5, 1, True)):
+        same(ours.get_pix_neigh(i, j, eight), ref.get_pix_neigh(i, j, eight))
+
+    from PIL import Image as PILImage
+    for name, arr in (('img.png', grey), ('mask.png', (rng.random(grey.shape) > 0.3).astype(np.uint8) * 255), ('gt.png', truth)):
+        PILImage.fromarray(arr).save(tmp_path / name)
+    objs = []
+    for mod in (ours, ref):
+        im = mod.Image()
+        im.load(str(tmp_path), 'img.png')
+        im.load_mask(str(tmp_path), lambda f: 'mask.png')
+        im.load_ground_truth(str(tmp_path), lambda f: 'gt.png')
+        im.apply_mask()
+        twin = im.__copy__()
+        twin.apply_clahe()
+        objs.append((im, twin))
+    (a, a2), (b, b2) = objs
+    same(a.array, b.array), same(a.mask, b.mask), same(a.ground_truth, b.ground_truth)
+    same(a2.array, b2.array)
+    assert a2.array is not a.array and (a.array[a.mask == 0] == 0).all()
+    same(a.get_array(str(tmp_path), lambda f: 'gt.png'), b.get_array(str(tmp_path), lambda f: 'gt.png'))
+
+
+def test_leaf_components_match_the_reference_on_random_inputs(tmp_path):
+    """Metrics, loss, model-selection helpers, the padded sampler and both split generators, each against the reference's own
+    implementation on the same random inputs (not against hand-copied golden numbers)."""
+    _reference_or_skip()
+    import coinstac_dinunet.metrics as rmet
+    from coinstac_dinunet.metrics.loss import dice_loss_binary as ref_dice
+    from coinstac_dinunet.utils.utils import performance_improved_ as ref_improved, stop_training_ as ref_stop
+    from coinstac_dinunet.data.data import COINNPaddedDataSampler as RefSampler
+    from coinstac_dinunet.data import datautils as rdu
+    import coinstac_dinunet_b200.metrics as omet
+    from coinstac_dinunet_b200.metrics.loss import dice_loss_binary as our_dice
+    from coinstac_dinunet_b200.utils import performance_improved_ as our_improved, stop_training_ as our_stop
+    from coinstac_dinunet_b200.data import COINNPaddedDataSampler as OurSampler
+    from coinstac_dinunet_b200.data import datautils as odu
+    g = torch.Generator().manual_seed(9)
+
+    # ---- Prf1a / COINNAverages: add, accumulate, get, serialize, reduce_sites
+    for _ in range(5):
+        n = int(torch.randint(1, 200, (1,), generator=g))
+        pred, true = torch.randint(0, 2, (n,), generator=g), torch.randint(0, 2, (n,), generator=g)
+        r, o = rmet.Prf1a(), omet.Prf1a()
+        r.add(pred, true), o.add(pred, true)
+        r2, o2 = rmet.Prf1a(), omet.Prf1a()
+        r2.add(1 - pred, true), o2.add(1 - pred, true)
+        r.accumulate(r2), o.accumulate(o2)
+        assert o.get() == pytest.approx(r.get(), abs=1e-9) and o.serialize() == pytest.approx(r.serialize(), abs=1e-9)
+        assert (o.tp, o.fp, o.tn, o.fn) == (r.tp, r.fp, r.tn, r.fn) and o.overlap == pytest.approx(r.overlap)
+        assert o.f_beta(2) == pytest.approx(r.f_beta(2))
+        rr, oo = rmet.Prf1a(), omet.Prf1a()
+        rr.reduce_sites([r.serialize(), r2.serialize()]), oo.reduce_sites([o.serialize(), o2.serialize()])
+        assert oo.get() == pytest.approx(rr.get(), abs=1e-9)
+    ra, oa = rmet.COINNAverages(num_averages=2), omet.COINNAverages(num_averages=2)
+    for i in range(6):
+        v, n = float(torch.randn((), generator=g)), int(torch.randint(1, 9, (1,), generator=g))
+        ra.add(v, n, index=i % 2), oa.add(v, n, index=i % 2)
+    assert oa.get() == pytest.approx(ra.get(), abs=1e-6) and np.allclose(np.asarray(oa.serialize(), float),
+                                                                        np.asarray(ra.serialize(), float), atol=1e-6)
+
+    # ---- ConfusionMatrix (local scores; the reference's remote aggregation is the broken path of SURVEY 8.5-7)
+    C = 4
+    pred, true = torch.randint(0, C, (300,), generator=g), torch.randint(0, C, (300,), generator=g)
+    rc, oc = rmet.ConfusionMatrix(num_classes=C), omet.ConfusionMatrix(num_classes=C)
+    rc.add(pred, true), oc.add(pred, true)
+    assert torch.equal(oc.matrix, rc.matrix)
+    # (the reference's own .get() raises on current torch - round() of a 0-d tensor - so compare the scores it is built from)
+    want = [float(rc.accuracy()), float(rc.f1()), float(rc.precision()), float(rc.recall())]
+    assert oc.get() == pytest.approx(want, abs=1e-5)
+    assert [float(x) for x in oc.precision(False)] == pytest.approx([float(x) for x in rc.precision(False)], abs=1e-6)
+    assert [float(x) for x in oc.recall(False)] == pytest.approx([float(x) for x in rc.recall(False)], abs=1e-6)
+
+    # ---- AUC (sklearn inside the reference)
+    prob, lab = torch.rand(400, generator=g), torch.randint(0, 2, (400,), generator=g)
+    prob[::7] = 0.5                                         # ties
+    rauc, oauc = rmet.AUCROCMetrics(), omet.AUCROCMetrics()
+    try:
+        rauc.add(prob, lab)
+        want = rauc.auc()
+    except Exception:  # noqa: BLE001   (scikit-learn missing)
+        want = None
+    if want is not None:
+        oauc.add(prob, lab)
+        assert float(oauc.auc()) == pytest.approx(float(want), abs=1e-5)
+
+    # ---- dice loss, model selection, early stopping
+    out, tgt = torch.rand(3, 1, 9, 9, generator=g), (torch.rand(3, 1, 9, 9, generator=g) > 0.5).float()
+    for beta in (1, 2):
+        assert float(our_dice(out, tgt, beta=beta)) == pytest.approx(float(ref_dice(out, tgt, beta=beta)), abs=1e-6)
+    for direction in ('maximize', 'minimize'):
+        c1 = {'metric_direction': direction, 'best_val_score': 0.5, 'best_val_epoch': 0, 'epochs': 10, 'patience': 3}
+        c2 = dict(c1)
+        for epoch, score in enumerate([0.5, 0.50005, 0.6, 0.4, 0.39, 0.7, 0.7, 0.1], 1):
+            assert our_improved(epoch, score, c2) == ref_improved(epoch, score, c1)
+            assert our_stop(epoch, c2) == ref_stop(epoch, c1)
+            assert c1 == c2
+
+    # ---- padded sampler: the reference never shuffles a second epoch differently unless set_epoch is called - same here
+    class Sized:
+        def __init__(self, n):
+            self.n = n
+
+        def __len__(self):
+            return self.n
+    for n, bs in ((10, 4), (3, 8), (17, 5), (16, 4), (1, 3)):
+        for shuffle in (False, True):
+            for drop in (False, True):
+                r = RefSampler(Sized(n), bs, seed=3, shuffle=shuffle, drop_last=drop)
+                o = OurSampler(Sized(n), bs, seed=3, shuffle=shuffle, drop_last=drop)
+                for epoch in (0, 2):
+                    r.set_epoch(epoch), o.set_epoch(epoch)
+                    assert list(o) == list(r) and len(o) == len(r)
+
+    # ---- split generators write the same files
+    files = [f'subj_{i:03d}.npy' for i in range(23)]
+    for kind, cache in (('ratio3', {'split_ratio': [0.6, 0.2, 0.2]}), ('ratio2', {'split_ratio': [0.75, 0.25]}),
+                        ('kfold', {'num_folds': 5})):
+        outs = []
+        for tag, mod in (('ref', rdu), ('ours', odu)):
+            d = tmp_path / f'{kind}_{tag}'
+            d.mkdir()
+            c = dict(cache, split_dir=str(d))
+            (mod.create_k_fold_splits if 'num_folds' in cache else mod.create_ratio_split)(list(files), c)
+            outs.append({f: json.load(open(d / f)) for f in sorted(os.listdir(d))})
+        assert outs[0] == outs[1] and outs[0]
