@@ -351,3 +351,70 @@ def test_leaf_components_match_the_reference_on_random_inputs(tmp_path):
             (mod.create_k_fold_splits if 'num_folds' in cache else mod.create_ratio_split)(list(files), c)
             outs.append({f: json.load(open(d / f)) for f in sorted(os.listdir(d))})
         assert outs[0] == outs[1] and outs[0]
+
+
+def test_utils_and_wire_helpers_match_the_reference(tmp_path):
+    """``FrozenDict``, score CSVs, ``logs.json``, ``lazy_debug``, ``safe_concat``, seeded weight init (on the layer types the
+    reference initialises) and the gradient wire files, reference vs ours."""
+    _reference_or_skip()
+    import coinstac_dinunet.utils as ru
+    import coinstac_dinunet.utils.tensorutils as rtu
+    import coinstac_dinunet_b200.utils as ou
+    import coinstac_dinunet_b200.utils.tensorutils as otu
+
+    for mod in (ru, ou):
+        fd = mod.FrozenDict({'a': 1})
+        fd['b'] = 2
+        fd.update(c=3)
+        with pytest.raises(ValueError):
+            fd['a'] = 5
+        with pytest.raises(ValueError):
+            fd.update(b=7)
+        assert dict(fd) == {'a': 1, 'b': 2, 'c': 3}
+    assert [ou.lazy_debug(x) for x in range(1, 400)] == [ru.lazy_debug(x) for x in range(1, 400)]
+    assert [ou.lazy_debug(x, 3) for x in range(1, 400)] == [ru.lazy_debug(x, 3) for x in range(1, 400)]
+
+    cache = {'log_header': 'Loss|Accuracy,F1', 'test_metrics': [[0.51234, 0.9, 0.8], [0.4, 1.0, 1.0]], 'note': ['a', 'b'],
+             'nested': {'t': torch.ones(1), 'ok': 1.5, 'lst': [{'x': {1, 2}}]}, 'obj': object, 'none': None}
+    texts = []
+    for tag, mod in (('ref', ru), ('ours', ou)):
+        d = tmp_path / tag
+        d.mkdir()
+        mod.save_scores(dict(cache), str(d), file_keys=['test_metrics', 'note'])
+        mod.save_cache({**cache, 'nested': {**cache['nested']}}, str(d))
+        logs = json.load(open(d / 'logs.json'))
+        texts.append((open(d / 'test_metrics.csv').read(), open(d / 'note.csv').read(), logs))
+    assert texts[0][0] == texts[1][0] and texts[0][1] == texts[1][1]
+    assert texts[0][2].keys() == texts[1][2].keys()
+    for k in ('log_header', 'test_metrics', 'note', 'none'):
+        assert texts[0][2][k] == texts[1][2][k]
+    assert texts[1][2]['nested']['ok'] == 1.5 and isinstance(texts[1][2]['nested']['t'], str)
+
+    g = torch.Generator().manual_seed(1)
+    for big, small in (((2, 3, 11, 12), (2, 5, 8, 9)), ((1, 2, 9, 9, 9), (1, 4, 6, 6, 6))):
+        a, b = torch.randn(big, generator=g), torch.randn(small, generator=g)
+        assert torch.equal(otu.safe_concat(a, b), rtu.safe_concat(a, b))
+
+    def net():
+        return torch.nn.Sequential(torch.nn.Conv2d(2, 4, 3), torch.nn.BatchNorm2d(4), torch.nn.Flatten(),
+                                   torch.nn.Linear(16, 8), torch.nn.Linear(8, 2, bias=False))
+    m_ref, m_our = net(), net()
+    torch.manual_seed(21)
+    rtu.initialize_weights(m_ref)
+    torch.manual_seed(21)
+    otu.initialize_weights(m_our, extended=False)
+    for (n, p), (_, q) in zip(m_ref.state_dict().items(), m_our.state_dict().items()):
+        assert torch.equal(p, q), n
+
+    x = torch.randn(3, 2, 4, 4, generator=g)
+    for m in (m_ref, m_our):
+        m(x).square().mean().backward()
+    for dtype in ('float32', 'float16'):
+        gr, go = rtu.extract_grads(m_ref, dtype), otu.extract_grads(m_our, dtype)
+        assert all(a.dtype == b.dtype and np.array_equal(a, b) for a, b in zip(gr, go))
+        rtu.save_arrays(str(tmp_path / 'ref.npy'), np.array(gr, dtype=object))
+        otu.save_arrays(str(tmp_path / 'ours.npy'), otu.as_object_array(go))
+        for reader in (rtu.load_arrays, otu.load_arrays):                # each side reads the other's file
+            for path in ('ref.npy', 'ours.npy'):
+                back = reader(str(tmp_path / path))
+                assert all(np.array_equal(a, b) for a, b in zip(back, gr))
