@@ -49,9 +49,8 @@ def _make_engine(tmp, tag):
     return eng
 
 
-def _run_reference(eng):
-    """The reference's own COINNLocal / COINNRemote / COINNTrainer / COINNDataset, stock dSGD learner + reducer."""
-    from multiprocessing.pool import ThreadPool
+def _reference_classes():
+    """The reference's own node classes plus the two user classes a computation author writes against them."""
     import torch.nn.functional as F
     from coinstac_dinunet import COINNDataset, COINNLocal, COINNRemote, COINNTrainer
     from coinstac_dinunet.data import COINNDataHandle
@@ -82,7 +81,13 @@ def _run_reference(eng):
             score.add(pred, y)
             val.add(loss.item(), len(x))
             return {'out': out, 'loss': loss, 'averages': val, 'metrics': score, 'prediction': pred}
+    return COINNLocal, COINNRemote, RefTrainer, RefData, COINNDataHandle
 
+
+def _run_reference(eng):
+    """The reference's own COINNLocal / COINNRemote / COINNTrainer / COINNDataset, stock dSGD learner + reducer."""
+    from multiprocessing.pool import ThreadPool
+    COINNLocal, COINNRemote, RefTrainer, RefData, COINNDataHandle = _reference_classes()
     pool = ThreadPool(2)
     try:
         def local_fn(site, cache, inp, state):
@@ -448,3 +453,44 @@ def test_rankdad_engine_follows_the_reference_protocol(tmp_path, monkeypatch):
     a0 = our_eng.site_cache['local0']['nn']['fs_net'].state_dict()
     a1 = our_eng.site_cache['local1']['nn']['fs_net'].state_dict()
     assert all(torch.equal(a0[k], a1[k]) for k in a0 if 'running_' not in k and 'num_batches' not in k)
+
+
+@pytest.mark.parametrize('aggregator', ['ours', 'reference'])
+def test_mixed_deployment_reference_site_and_our_site_interoperate(tmp_path, aggregator):
+    """Wire compatibility, end to end: ONE consortium in which site ``local0`` runs the unmodified reference package and site
+    ``local1`` runs this framework, under either implementation's aggregator.  Same JSON keys, same ``grads.npy`` /
+    ``avg_grads.npy`` object arrays, same phase protocol - the run completes all folds and the two sites' parameters are
+    bit-identical after every fold."""
+    _reference_or_skip()
+    from multiprocessing.pool import ThreadPool
+    import coinstac_dinunet_b200 as ours
+    from coinstac_dinunet_b200.models import FSVDataset, FSVTrainer
+    RefLocal, RefRemote, RefTrainer, RefData, RefDataHandle = _reference_classes()
+    eng = _make_engine(tmp_path, 'mixed')
+    pool = ThreadPool(2)
+    per_fold = []
+    norm = lambda v: str(getattr(v, 'value', v)).split('.')[-1].lower()
+
+    def local_fn(site, cache, inp, state):
+        if site == 'local0':
+            return RefLocal(cache=cache, input=inp, state=state)(pool, RefTrainer, RefData, RefDataHandle)
+        return ours.COINNLocal(cache=cache, input=inp, state=state)(pool, FSVTrainer, FSVDataset, ours.COINNDataHandle)
+
+    def remote_fn(cache, inp, state):
+        if all(norm(v.get('phase')) == 'next_run_waiting' for v in inp.values()):      # a fold just finished on every site
+            a = eng.site_cache['local0']['nn']['fs_net'].state_dict()
+            b = eng.site_cache['local1']['nn']['fs_net'].state_dict()
+            per_fold.append(all(torch.equal(a[k], b[k]) for k in a if 'running_' not in k and 'num_batches' not in k))
+        if aggregator == 'reference':
+            return RefRemote(cache=cache, input=inp, state=state, num_class=2, seed=7)(pool, RefTrainer)
+        return ours.COINNRemote(cache=cache, input=inp, state=state, num_class=2, seed=7)(pool, FSVTrainer)
+
+    try:
+        eng.run(local_fn, remote_fn, max_rounds=3000)
+    finally:
+        pool.terminate()
+    assert norm(eng.trace[-2]['remote']) == 'success'
+    assert per_fold == [True, True, True]
+    for site in eng.site_ids:                                   # both sites received the aggregator's results archive
+        out = eng.site_state[site]['outputDirectory']
+        assert any(f.endswith('.zip') for f in os.listdir(out)), site
