@@ -3,7 +3,9 @@ splits, shard ownership, metric additivity, the MX-FP8 quantisation rule, wire f
 import numpy as np
 import pytest
 import torch
-from hypothesis import assume, given, settings, strategies as st
+
+pytest.importorskip('hypothesis')
+from hypothesis import assume, given, settings, strategies as st  # noqa: E402
 
 from coinstac_dinunet_b200.data import COINNPaddedDataSampler
 from coinstac_dinunet_b200.data.datautils import create_k_fold_splits, create_ratio_split
