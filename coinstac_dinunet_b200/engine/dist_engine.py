@@ -116,6 +116,7 @@ class DistEngine:
                 if mb is not None:
                     mb.close()
                 return None
+            mb.verify_pids()                                # every rank has attached (the vote above was the rendezvous)
             atexit.register(mb.close)
             grp = self.ctl
 

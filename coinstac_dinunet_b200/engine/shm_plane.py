@@ -64,6 +64,7 @@ class ShmMailbox:
             except Exception:
                 pass
         _struct.pack_into('<Q', self.mem.buf, self.rank * self.slot + 16, _os.getpid())
+        self.check_pids = True
         self.seq = 0           # messages this rank has posted
         self.answers = 0       # aggregator answers consumed / posted
 
@@ -106,12 +107,22 @@ class ShmMailbox:
         for r in range(self.world):
             if _struct.unpack_from('<Q', self.mem.buf, r * self.slot + 24)[0]:
                 raise PeerFailure(f'control plane: rank {r} aborted the run')
-        if not liveness:
+        if not (liveness and self.check_pids):
             return
         writer = 0 if slot == self.world else slot
         pid = _struct.unpack_from('<Q', self.mem.buf, writer * self.slot + 16)[0]
         if pid and pid != _os.getpid() and not _alive(pid):
             raise PeerFailure(f'control plane: rank {writer} (pid {pid}) is gone')
+
+    def verify_pids(self):
+        """Call once every rank has attached: the liveness check is only meaningful when the ranks share a PID namespace.  If
+        any recorded pid is not visible from here (ranks in different containers over one /dev/shm) the check is switched
+        off for this rank - the abort word and the timeout still apply."""
+        for r in range(self.world):
+            pid = _struct.unpack_from('<Q', self.mem.buf, r * self.slot + 16)[0]
+            if not pid or not _alive(pid):
+                self.check_pids = False
+        return self.check_pids
 
     def abort(self):
         """Tell every waiting rank that this one is not going to post again."""
