@@ -6,8 +6,8 @@ user's ``trainer.iteration(batch)`` is captured once - with whatever metric obje
 replayed; per-step scores are pushed, inside the graph, into a device ring buffer and read back once per
 epoch (``drain``), so a training round performs zero host syncs.
 
-Requirements: static batch shapes (the padded sampler guarantees them), ``local_iterations == 1``, metric
-objects that expose ``device_state()`` (COINNAverages / Prf1a / ConfusionMatrix do).
+Requirements: static batch shapes (the padded sampler guarantees them), ``local_iterations == 1``, the built-in
+metric objects (COINNAverages / Prf1a / ConfusionMatrix keep their per-step counters in device tensors).
 """
 import torch as _torch
 
