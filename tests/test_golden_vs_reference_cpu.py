@@ -494,3 +494,68 @@ def test_mixed_deployment_reference_site_and_our_site_interoperate(tmp_path, agg
     for site in eng.site_ids:                                   # both sites received the aggregator's results archive
         out = eng.site_state[site]['outputDirectory']
         assert any(f.endswith('.zip') for f in os.listdir(out)), site
+
+
+def test_public_api_names_and_signatures_cover_the_reference():
+    """Mechanical parity check: every module-level function / class / method / constant the installed reference
+    defines exists here under the same module path, and every public callable accepts the reference's positional parameters
+    in the reference's order (extra trailing parameters and **kw are allowed)."""
+    import ast
+    ref_root = os.path.join(ROOT, 'baseline', '_ref', 'coinstac_dinunet')
+    our_root = os.path.join(ROOT, 'coinstac_dinunet_b200')
+    if not os.path.isdir(ref_root):
+        pytest.skip('reference not installed under baseline/_ref')
+
+    def scan(path, reexports=False):
+        names, sigs = set(), {}
+        tree = ast.parse(open(path).read())
+
+        def params(fn):
+            a = fn.args
+            return [x.arg for x in a.posonlyargs + a.args], a.kwarg is not None
+
+        for node in tree.body:
+            if isinstance(node, (ast.FunctionDef, ast.AsyncFunctionDef)):
+                names.add(node.name)
+                sigs[node.name] = params(node)
+            elif isinstance(node, ast.ClassDef):
+                names.add(node.name)
+                for sub in node.body:
+                    if isinstance(sub, (ast.FunctionDef, ast.AsyncFunctionDef)):
+                        names.add(f'{node.name}.{sub.name}')
+                        sigs[f'{node.name}.{sub.name}'] = params(sub)
+            elif isinstance(node, ast.Assign):
+                for t in node.targets:
+                    for leaf in (t.elts if isinstance(t, ast.Tuple) else [t]):
+                        if isinstance(leaf, ast.Name):
+                            names.add(leaf.id)
+            elif reexports and isinstance(node, ast.ImportFrom):     # re-exports count (`from .logger import lazy_debug`)
+                names.update(a.asname or a.name for a in node.names)
+        return names, sigs
+
+    internal = {'DADParallel._hierarchy_key', 'DADParallel._hook_fn'}      # private helpers of the reference's hook plumbing
+    missing, mismatched, checked = [], [], 0
+    for base, _dirs, files in os.walk(ref_root):
+        for f in files:
+            if not f.endswith('.py'):
+                continue
+            rel = os.path.relpath(os.path.join(base, f), ref_root)
+            ours = os.path.join(our_root, rel)
+            if not os.path.exists(ours):
+                missing.append((rel, '<module>'))
+                continue
+            r_names, r_sigs = scan(os.path.join(base, f))
+            o_names, o_sigs = scan(ours, reexports=True)
+            missing += [(rel, n) for n in sorted(r_names - o_names - internal) if not n.startswith('_')
+                        or n in ('__call__', '__init__')]
+            for name, (r_pos, _) in r_sigs.items():
+                leaf = name.split('.')[-1]
+                if name not in o_sigs or (leaf.startswith('_') and leaf not in ('__init__', '__call__')):
+                    continue
+                o_pos, o_kw = o_sigs[name]
+                checked += 1
+                if o_pos[:len(r_pos)] != r_pos and not (o_kw and set(r_pos) <= set(o_pos)):
+                    mismatched.append((rel, name, r_pos, o_pos))
+    assert not missing, missing
+    assert not mismatched, mismatched
+    assert checked > 150
