@@ -104,7 +104,9 @@ def test_control_plane_mailbox_detects_a_failed_peer(behaviour):
         assert mb.gather({'round': 1}) == [{'round': 1}, {'round': 1}]
         mb.broadcast('ack')
         if behaviour == 'zombie':                       # dead but not reaped by its launcher yet: /proc/<pid>/stat says Z
+            deadline = time.monotonic() + 60
             while open(f'/proc/{proc.pid}/stat').read().rsplit(')', 1)[1].split()[0] != 'Z':
+                assert time.monotonic() < deadline, 'the peer process never exited'
                 time.sleep(0.01)
         else:
             proc.wait(30)                               # reaped: the pid is really gone
