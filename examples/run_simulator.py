@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run an example computation in the in-process engine on synthetic sites:  python examples/run_simulator.py fsv|vbm"""
+"""Run an example computation in the in-process engine on synthetic sites:  python examples/run_simulator.py fsv|vbm|custom"""
 import importlib.util
 import os
 import sys
@@ -13,6 +13,9 @@ from coinstac_dinunet_b200.models import write_synthetic_site  # noqa: E402
 
 
 def _load(path, name):
+    here = os.path.dirname(path)
+    if here not in sys.path:                 # entry scripts may import their siblings (`from local import MyTrainer`)
+        sys.path.insert(0, here)
     spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
@@ -21,6 +24,7 @@ def _load(path, name):
 
 def main(which='fsv', n_sites=2):
     here = os.path.join(ROOT, 'examples', which)
+    sys.modules.pop('local', None)          # a sibling import of another example must not be reused
     local, remote = _load(os.path.join(here, 'local.py'), f'{which}_local'), _load(os.path.join(here, 'remote.py'), f'{which}_remote')
     shape = (66,) if which == 'fsv' else (1, 33, 37, 33)
     spec = dict(mode='train', data_dir='data', labels_file='labels.json', num_class=2, split_ratio=[0.6, 0.2, 0.2],

@@ -100,8 +100,9 @@ def test_example_computations_run_in_the_simulator():
     spec = importlib.util.spec_from_file_location('run_simulator', os.path.join(root, 'examples', 'run_simulator.py'))
     sim = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(sim)
-    eng = sim.main('fsv')
-    assert eng.trace[-2]['remote'] == 'success'
+    for which in ('fsv', 'vbm', 'custom'):                   # (custom: local.py / remote.py import each other as siblings)
+        eng = sim.main(which)
+        assert eng.trace[-2]['remote'] == 'success', which
     assert json.load(open(os.path.join(root, 'examples', 'vbm', 'compspec.json')))['computation']['input']['transport']['default'] == 'nvlink'
 
 
